@@ -1,0 +1,241 @@
+"""Kernel-level CPU oracle for the B200 formulation.  TEST INFRASTRUCTURE ONLY.
+
+The CUDA path does not replay the reference's H1 / Givens / H2 column step
+(unblocked.cc:53-128); it uses ONE quaternion Householder reflector per column, which
+reaches the same tridiagonal form Q^H M Q = diag(T, T*) that blocked.cc:42-68 targets.
+This module restates every device kernel of that formulation in numpy so the
+`-m gpu` tests can compare kernel by kernel (K1 mat-vec, panel, K4 trailing update,
+phase chain, T factor, K6 back-transform, K10 pairing).  The whole chain is itself
+checked against the reference (oracle/_ref) in tests/test_oracle.py.
+
+Conventions: a quaternion q = a + j b is the complex pair (a, b);
+matrices act from the left, scalars multiply vectors from the right;
+Phi(D,E) = [[D, -conj(E)], [E, conj(D)]].
+"""
+from __future__ import annotations
+
+import numpy as np
+
+c = np.conj
+
+
+def qmul(p, q):
+    (a, b), (cc, d) = p, q
+    return a * cc - c(b) * d, b * cc + c(a) * d
+
+
+def qconj(p):
+    a, b = p
+    return c(a), -b
+
+
+def matvec_full(D, E, va, vb):
+    """K1 semantics on full storage: y = (D + jE)(va + j vb)."""
+    return D @ va - c(E) @ vb, E @ va + c(D) @ vb
+
+
+def matvec_lower(D, E, va, vb):
+    """K1 as the device kernel computes it: only the LOWER triangles of D (Hermitian,
+    real diagonal) and E (antisymmetric, zero diagonal) are read."""
+    Dl = np.tril(D, -1)
+    El = np.tril(E, -1)
+    dg = D.diagonal().real
+    ya = Dl @ va - c(El) @ vb + c(Dl).T @ va + c(El).T @ vb + dg * va
+    yb = El @ va + c(Dl) @ vb - El.T @ va + Dl.T @ vb + dg * vb
+    return ya, yb
+
+
+def PH(Xa, Xb, ya, yb):
+    """X^H y for a quaternion panel X and quaternion vector y."""
+    return c(Xa).T @ ya + c(Xb).T @ yb, Xa.T @ yb - Xb.T @ ya
+
+
+def PV(Xa, Xb, ca, cb):
+    """X c for a quaternion panel X and quaternion coefficient vector c."""
+    return Xa @ ca - c(Xb) @ cb, Xb @ ca + c(Xa) @ cb
+
+
+def make_reflector(xa, xb):
+    """Quaternion Householder: H = I - tau v v^H (tau REAL, v[0] = 1) with H x = e1 alpha.
+    Returns (alpha_a, alpha_b, tau, va, vb)."""
+    nx2 = float(np.sum(xa.real ** 2 + xa.imag ** 2 + xb.real ** 2 + xb.imag ** 2))
+    x1 = np.sqrt(abs(xa[0]) ** 2 + abs(xb[0]) ** 2)
+    rest2 = nx2 - x1 * x1
+    va, vb = xa.copy(), xb.copy()
+    if nx2 == 0.0 or (rest2 <= 0.0 and len(xa) == 1 and False):
+        va[:] = 0
+        vb[:] = 0
+        va[0] = 1.0
+        return 0j, 0j, 0.0, va, vb
+    nx = np.sqrt(nx2)
+    if x1 == 0.0:
+        pa, pb = 1.0 + 0j, 0j
+    else:
+        pa, pb = xa[0] / x1, xb[0] / x1
+    al_a, al_b = -pa * nx, -pb * nx
+    u1a, u1b = xa[0] - al_a, xb[0] - al_b
+    u1n2 = abs(u1a) ** 2 + abs(u1b) ** 2
+    # ||u||^2 = ||x||^2 + 2 |x1| ||x|| + ||x||^2 - ... computed directly
+    un2 = nx2 - x1 * x1 + u1n2
+    tau = 2.0 * u1n2 / un2
+    ia, ib = c(u1a) / u1n2, -u1b / u1n2          # u1^{-1}
+    va, vb = qmul((xa, xb), (ia, ib))              # right scale
+    va[0], vb[0] = 1.0, 0.0
+    return al_a, al_b, tau, va, vb
+
+
+def tridiagonalise(D, E, nb):
+    """Blocked reduction (panel + stacked rank-2k update), lower triangles only.
+
+    Returns d[n], alpha_a[n-1], alpha_b[n-1], tau[n-1] and the arrays D, E whose strictly
+    sub-sub-diagonal parts now hold the reflector tails v[1:] (v[0] = 1 implicit)."""
+    D = D.copy()
+    E = E.copy()
+    n = D.shape[0]
+    d = np.zeros(n)
+    ala = np.zeros(max(n - 1, 0), dtype=np.complex128)
+    alb = np.zeros(max(n - 1, 0), dtype=np.complex128)
+    tau = np.zeros(max(n - 1, 0))
+    for j0 in range(0, n - 1, nb):
+        kb = min(nb, n - 1 - j0)
+        Va = np.zeros((n, kb), dtype=np.complex128)
+        Vb = np.zeros_like(Va)
+        Wa = np.zeros_like(Va)
+        Wb = np.zeros_like(Va)
+        for i in range(kb):
+            k = j0 + i
+            ca, cb = D[k:, k].copy(), E[k:, k].copy()
+            if i > 0:
+                qa, qb = qconj((Wa[k, :i], Wb[k, :i]))
+                ta, tb = PV(Va[k:, :i], Vb[k:, :i], qa, qb)
+                ca -= ta
+                cb -= tb
+                qa, qb = qconj((Va[k, :i], Vb[k, :i]))
+                ta, tb = PV(Wa[k:, :i], Wb[k:, :i], qa, qb)
+                ca -= ta
+                cb -= tb
+            d[k] = ca[0].real
+            al_a, al_b, t, va, vb = make_reflector(ca[1:], cb[1:])
+            ala[k], alb[k], tau[k] = al_a, al_b, t
+            D[k + 1:, k] = va
+            E[k + 1:, k] = vb
+            fa = np.zeros(n, dtype=np.complex128)
+            fb = np.zeros(n, dtype=np.complex128)
+            fa[k + 1:], fb[k + 1:] = va, vb
+            # mat-vec with the matrix as of the START of the panel, trailing block only
+            pa = np.zeros(n, dtype=np.complex128)
+            pb = np.zeros(n, dtype=np.complex128)
+            pa[k + 1:], pb[k + 1:] = matvec_lower(D[k + 1:, k + 1:], E[k + 1:, k + 1:], va, vb)
+            if i > 0:
+                ga, gb = PH(Wa[:, :i], Wb[:, :i], fa, fb)
+                ta, tb = PV(Va[:, :i], Vb[:, :i], ga, gb)
+                pa -= ta
+                pb -= tb
+                ga, gb = PH(Va[:, :i], Vb[:, :i], fa, fb)
+                ta, tb = PV(Wa[:, :i], Wb[:, :i], ga, gb)
+                pa -= ta
+                pb -= tb
+            pa *= t
+            pb *= t
+            pa[:k + 1] = 0
+            pb[:k + 1] = 0
+            g = float((np.vdot(fa, pa) + np.vdot(fb, pb)).real)
+            Va[:, i], Vb[:, i] = fa, fb
+            Wa[:, i] = pa - 0.5 * t * g * fa
+            Wb[:, i] = pb - 0.5 * t * g * fb
+        r0 = j0 + kb
+        if r0 < n:
+            L = np.block([[Va[r0:], c(Vb[r0:]), Wa[r0:], c(Wb[r0:])],
+                          [Vb[r0:], -c(Va[r0:]), Wb[r0:], -c(Wa[r0:])]])
+            R = np.hstack([Wa[r0:], c(Wb[r0:]), Va[r0:], c(Vb[r0:])])
+            U = L @ c(R).T
+            m = n - r0
+            D[r0:, r0:] -= np.tril(U[:m])
+            E[r0:, r0:] -= np.tril(U[m:], -1)
+    d[n - 1] = D[n - 1, n - 1].real
+    return d, ala, alb, tau, D, E
+
+
+def phase_chain(ala, alb):
+    """s_0 = 1, s_{k+1} = (alpha_k / |alpha_k|) s_k -- the diagonal unit-quaternion
+    similarity that makes the quaternion tridiagonal real symmetric (e_k = |alpha_k|)."""
+    n = len(ala) + 1
+    sa = np.zeros(n, dtype=np.complex128)
+    sb = np.zeros(n, dtype=np.complex128)
+    sa[0] = 1.0
+    e = np.sqrt(np.abs(ala) ** 2 + np.abs(alb) ** 2)
+    for k in range(n - 1):
+        if e[k] == 0.0:
+            sa[k + 1], sb[k + 1] = sa[k], sb[k]
+        else:
+            sa[k + 1], sb[k + 1] = qmul((ala[k] / e[k], alb[k] / e[k]), (sa[k], sb[k]))
+            nrm = np.sqrt(abs(sa[k + 1]) ** 2 + abs(sb[k + 1]) ** 2)
+            sa[k + 1] /= nrm
+            sb[k + 1] /= nrm
+    return e, sa, sb
+
+
+def phi_panel(D, E, j0, kb):
+    """Phi(V) for the reflectors of panel [j0, j0+kb): complex (2m x 2kb), rows j0+1..n-1,
+    m = n-1-j0; columns [V | Theta V] = [[Va, -conj(Vb)], [Vb, conj(Va)]]."""
+    n = D.shape[0]
+    m = n - 1 - j0
+    Va = np.zeros((m, kb), dtype=np.complex128)
+    Vb = np.zeros((m, kb), dtype=np.complex128)
+    for i in range(kb):
+        Va[i, i] = 1.0
+        Va[i + 1:, i] = D[j0 + i + 2:, j0 + i]
+        Vb[i + 1:, i] = E[j0 + i + 2:, j0 + i]
+    return np.block([[Va, -c(Vb)], [Vb, c(Va)]])
+
+
+def tfactor(P, tau):
+    """Compact-WY T (2kb x 2kb complex, the Phi-image of the upper-triangular quaternion T)
+    with H_0 H_1 ... H_{kb-1} = I - P T P^H, column order of P = [V | Theta V]."""
+    kb = len(tau)
+    G = c(P).T @ P
+    T = np.zeros((2 * kb, 2 * kb), dtype=np.complex128)
+    for i in range(kb):
+        idx_prev = np.concatenate([np.arange(i), kb + np.arange(i)]).astype(int)
+        for col in (i, kb + i):
+            T[col, col] = tau[i]
+            if i > 0:
+                T[np.ix_(idx_prev, [col])] = -tau[i] * (T[np.ix_(idx_prev, idx_prev)] @ G[np.ix_(idx_prev, [col])])
+    return T
+
+
+def backtransform(D, E, tau, Xa, Xb, nb):
+    """K6: X <- H_0 H_1 ... H_{n-2} X, panel by panel in reverse order, as stacked complex
+    GEMMs on [Xa; Xb] with Phi(V)."""
+    n = D.shape[0]
+    X = np.vstack([Xa, Xb])
+    starts = list(range(0, n - 1, nb))
+    for j0 in reversed(starts):
+        kb = min(nb, n - 1 - j0)
+        m = n - 1 - j0
+        P = phi_panel(D, E, j0, kb)
+        T = tfactor(P, tau[j0:j0 + kb])
+        rows = np.concatenate([np.arange(j0 + 1, n), n + np.arange(j0 + 1, n)])
+        Y = c(P).T @ X[rows]
+        X[rows] -= P @ (T @ Y)
+    return X[:n], X[n:]
+
+
+def solve(M, nb=8, tridiag_solver=None):
+    """Whole B200 formulation on the CPU: returns (eig, out) like ts::zquatev."""
+    n = M.shape[0] // 2
+    D = np.array(M[:n, :n])
+    E = np.array(M[n:, :n])
+    d, ala, alb, tau, Df, Ef = tridiagonalise(D, E, nb)
+    e, sa, sb = phase_chain(ala, alb)
+    if tridiag_solver is None:
+        T = np.diag(d) + np.diag(e, -1) + np.diag(e, 1)
+        w, Z = np.linalg.eigh(T)
+    else:
+        w, Z = tridiag_solver(d, e)
+    Xa, Xb = sa[:, None] * Z, sb[:, None] * Z
+    Xa, Xb = backtransform(Df, Ef, tau, Xa, Xb, nb)
+    out = np.empty((2 * n, 2 * n), dtype=np.complex128)
+    out[:n, :n], out[n:, :n] = Xa, Xb
+    out[:n, n:], out[n:, n:] = -c(Xb), c(Xa)
+    return w, out
