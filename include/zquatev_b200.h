@@ -1,0 +1,99 @@
+/* zquatev_b200.h -- C ABI of the B200-native quaternionic Hermitian eigensolver.
+ *
+ * Drop-in boundary: the only public symbol of the reference is
+ *     int ts::zquatev(const int n2, std::complex<double>* const D, const int nld2, double* const eig)
+ * declared at reference zquatev.h:54 and defined at zquatev.cc:42-100.  `zquatev_b200` below has
+ * exactly those arguments and semantics with plain C types; include/zquatev.h re-declares
+ * ts::zquatev with the reference's signature and libzquatev_b200.so defines it by forwarding here,
+ * so the reference's own test.cc links against this library unmodified.
+ *
+ * Everything else in this header is an EXTENSION outside the reference symbol:
+ * eigenvalues-only mode, device-resident operands, batches, explicit plans, phase timings, and
+ * kernel-level test doors used by tests/ (-m gpu) to compare each CUDA kernel with oracle/.
+ *
+ * All matrices are column-major complex<double> (interleaved re,im), as in the reference.
+ * There is NO CPU fallback: every entry point needs a CUDA device (sm_100a build) and returns a
+ * negative code when the CUDA runtime reports an error.
+ */
+#ifndef ZQUATEV_B200_H
+#define ZQUATEV_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- return codes (the `info` of reference zquatev.cc:84,99) -------------------------------
+ *   0      success
+ *   > 0    the tridiagonal eigensolver failed or the input held NaN/Inf (the reference returns
+ *          zhbev's info > 0 in that case): 1 = non-finite tridiagonal,
+ *          2 = secular iteration limit, 4 = leaf QL iteration limit (bits may be OR-ed)
+ *   -1..-9 illegal argument number (LAPACK convention): -1 n2 odd or negative, -2 D null,
+ *          -3 ld2 < n2, -4 eig null
+ *   <= -1000  -(1000 + cudaError_t) CUDA runtime failure (no device, out of memory, ...)
+ */
+
+/* Replaces ts::zquatev (reference zquatev.h:54, zquatev.cc:42).
+ * n2   : dimension 2n of the complex matrix (even).
+ * D    : HOST array, ld2 x n2 complex<double>.  In : columns 0..n-1 hold (A; B) -- only the left
+ *        half is referenced (zquatev.h:45-46) and, inside it, only the lower triangles of A
+ *        (Hermitian) and B (antisymmetric).  Out: all 2n columns = ( U -V* ; V U* ).
+ * ld2  : leading dimension of D (>= n2).  Unlike the reference any ld2 >= n2 works.
+ * eig  : HOST array of >= n doubles; eig[0..n) ascending on return (only n values are written,
+ *        as in the reference).
+ */
+int zquatev_b200(int n2, void* D, int ld2, double* eig);
+
+typedef struct zq_options {
+  int jobz;          /* 1: eigenvalues + eigenvectors (default), 0: eigenvalues only            */
+  int device_ptrs;   /* 0: D and eig are host pointers, 1: device pointers (current device)    */
+  int nb;            /* panel width of the reduction (0 = library default; reference: 20,
+                        zquatev.cc:64)                                                          */
+  void* stream;      /* cudaStream_t to run on (NULL = the legacy default stream)               */
+  int sync;          /* device_ptrs only: 1 = wait for completion and return info (default when
+                        the struct is zero-initialised is 0 = asynchronous, info not checked)   */
+} zq_options;
+
+/* Same contract as zquatev_b200 plus options.  With jobz = 0 D is destroyed (holds reflectors). */
+int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt);
+
+/* `batch` independent problems of the same size (BASELINE config 5): problem b uses
+ * D + b*strideD (complex elements) and eig + b*strideEig; info[b] receives its return code.
+ * Host pointers.  The reference has no batched entry -- its callers loop over zquatev().      */
+int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig,
+                         long long strideEig, int* info);
+
+/* Workspace cache: plans (device workspaces for one n) are created on first use and cached per
+ * thread-safe global table; this frees them.                                                  */
+void zquatev_b200_release(void);
+
+/* Milliseconds of the phases of the LAST call on this thread's plan, measured with CUDA events
+ * on the solver's stream: [0] H2D, [1] tridiagonalisation, [2] tridiagonal eigensolver,
+ * [3] back-transformation + pairing, [4] D2H, [5] total device time, [6] K1 mat-vec launches
+ * (only when profiling is on), [7] number of kernel launches.  Returns 0 when no plan exists.  */
+int zquatev_b200_last_phases(double ms[8]);
+/* 1: also time every K1 launch with its own event pair (slower; for bench.py roofline).        */
+void zquatev_b200_set_profiling(int on);
+
+/* Library build info, e.g. "zquatev_b200 0.1 sm_100a nb=32".                                   */
+const char* zquatev_b200_version(void);
+
+/* ---- kernel-level test doors (device pointers; used only by tests/ and bench.py) ------------ */
+/* K1: y = (D + jE) v on rows/cols [s, n) reading only the lower triangles.
+ * A: 2n x n complex (lda), v,y: n quaternions (4 doubles each: a.re a.im b.re b.im), rows < s of v
+ * are ignored.  Returns the average device milliseconds per launch over `reps` launches.        */
+int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, void* y, int reps, double* ms);
+/* K4/K6 GEMM: C = alpha op(A) op(B) + beta C (complex).                                          */
+int zq_test_zgemm(int ta, int tb, int M, int N, int K, const double* alpha, const void* A, long long lda,
+                  const void* B, long long ldb, const double* beta, void* C, long long ldc, int lower, int reps,
+                  double* ms);
+/* K8: eigen-decomposition of the real symmetric tridiagonal (d, e): w[n] ascending, Z n x n (ld n). */
+int zq_test_stedc(int n, const double* d, const double* e, double* w, double* Z);
+/* K9: eigenvalues only by bisection.                                                             */
+int zq_test_bisect(int n, const double* d, const double* e, double* w);
+/* K1-K4: tridiagonalise A (2n x n, lda) in place; outputs d[n], e[n], tau[n], alpha[4n].          */
+int zq_test_tridiag(int n, int nb, void* A, long long lda, double* d, double* e, double* tau, double* alpha);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

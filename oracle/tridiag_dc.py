@@ -115,7 +115,7 @@ def secular_root(j, k, dl, z2, rho):
     return org, mu
 
 
-def merge(d, Q, off, n1, n2, rho_in, stats=None):
+def merge(d, Q, off, n1, n2, rho_in, stats=None, cores=None):
     """One rank-one merge on the diagonal block [off, off+n1+n2) of (d, Q), in place.
     On entry Q[blk] = diag(Q1, Q2) with eigenvalues d (any order inside each child);
     on exit the block holds the merged eigen-decomposition (columns in the order
@@ -134,6 +134,8 @@ def merge(d, Q, off, n1, n2, rho_in, stats=None):
     zs = z[order].copy()
     tol = 8.0 * EPS * max(np.max(np.abs(ds)), np.max(np.abs(zs)))
     nondefl, defl, rots = [], [], []
+    if cores is not None:
+        return _merge_with_cores(d, Q, sl, Qb, order, ds, zs, rho, nm, stats, cores)
     if rho * np.max(np.abs(zs)) <= tol:
         defl = list(range(nm))
     else:
@@ -201,13 +203,50 @@ def merge(d, Q, off, n1, n2, rho_in, stats=None):
     d[sl] = dn
 
 
+def _merge_with_cores(d, Q, sl, Qb, order, ds, zs, rho, nm, stats, cores):
+    """Same merge, but deflation scan and secular roots come from the C cores of the device
+    code compiled for the host (tests/host_shim) -- used to unit-test those cores on the CPU."""
+    k, dl, w, ndcol, dfval, dfcol, rots = cores.deflate(rho, ds, zs, order.astype(np.int32))
+    for (c1, c2, cc, s) in rots:
+        x, y = Qb[:, c1].copy(), Qb[:, c2].copy()
+        Qb[:, c1] = cc * x + s * y
+        Qb[:, c2] = cc * y - s * x
+    if stats is not None:
+        stats.append((nm, k))
+    Qn = np.zeros_like(Qb)
+    dn = np.zeros(nm)
+    if k > 0:
+        z2 = w * w
+        org, mu, worst = cores.secular(dl, z2, rho)
+        if stats is not None:
+            stats.append(("iters", worst))
+        S = (dl[:, None] - dl[org][None, :]) - mu[None, :]
+        lam = dl[org] + mu
+        zh = np.zeros(k)
+        for i in range(k):
+            p = S[i, i]
+            for jj in range(k):
+                if jj != i:
+                    p *= S[i, jj] / (dl[i] - dl[jj])
+            zh[i] = np.copysign(np.sqrt(abs(p)), w[i])
+        S = zh[:, None] / S
+        S /= np.linalg.norm(S, axis=0)[None, :]
+        Qn[:, :k] = Qb[:, ndcol] @ S
+        dn[:k] = lam
+    if nm - k:
+        Qn[:, k:] = Qb[:, dfcol]
+        dn[k:] = dfval
+    Q[sl, sl] = Qn
+    d[sl] = dn
+
+
 def leaf_solve(d, e):
     """Leaf eigen-solve; the device uses implicit-shift QL (dc_leaf.cu)."""
     T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
     return np.linalg.eigh(T)
 
 
-def stedc(d_in, e_in, leaf=LEAF, stats=None):
+def stedc(d_in, e_in, leaf=LEAF, stats=None, cores=None):
     """Eigen-decomposition of the real symmetric tridiagonal (d, e): returns (w ascending, Z)."""
     n = len(d_in)
     d = np.array(d_in, dtype=np.float64)
@@ -227,7 +266,10 @@ def stedc(d_in, e_in, leaf=LEAF, stats=None):
         d[p] -= abs(e[p - 1])
     Q = np.zeros((n, n))
     for off, s in levels[0]:
-        w, Zl = leaf_solve(d[off:off + s], e[off:off + s - 1])
+        if cores is not None:
+            w, Zl = cores.leaf(d[off:off + s], e[off:off + s - 1])
+        else:
+            w, Zl = leaf_solve(d[off:off + s], e[off:off + s - 1])
         d[off:off + s] = w
         Q[off:off + s, off:off + s] = Zl
     for li in range(1, len(levels)):
@@ -235,6 +277,6 @@ def stedc(d_in, e_in, leaf=LEAF, stats=None):
         for mi, (off, s) in enumerate(levels[li]):
             (o1, n1), (o2, n2) = child[2 * mi], child[2 * mi + 1]
             assert o1 == off and o2 == off + n1 and n1 + n2 == s
-            merge(d, Q, off, n1, n2, e[o2 - 1], stats)
+            merge(d, Q, off, n1, n2, e[o2 - 1], stats, cores)
     order = np.lexsort((np.arange(n), d))
     return d[order] * scale, Q[:, order]

@@ -1,0 +1,128 @@
+"""-m gpu: every CUDA kernel against its CPU restatement in oracle/ (through the C ABI test doors)."""
+import numpy as np
+import pytest
+
+from oracle import quat_kernels as K
+from oracle import tridiag_dc as T
+from oracle import zquatev_oracle as O
+from tests.test_oracle import _tri_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,s", [(1, 0), (5, 0), (5, 2), (64, 0), (64, 63), (130, 0), (130, 7), (257, 129), (700, 0),
+                                 (700, 333), (1031, 65)])
+def test_k1_matvec(n, s):
+    from tests import gpu_util as G
+    M = O.gen_sym(n, 100 + n)
+    rng = np.random.default_rng(n)
+    va = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    vb = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    ya, yb, _ = G.matvec(M, s, va, vb)
+    D, E = M[:n, :n], M[n:, :n]
+    ra, rb = K.matvec_lower(D[s:, s:], E[s:, s:], va[s:], vb[s:])
+    scale = np.linalg.norm(M) * np.linalg.norm(np.concatenate([va, vb]))
+    assert np.max(np.abs(ya[s:] - ra)) <= 1e-13 * scale
+    assert np.max(np.abs(yb[s:] - rb)) <= 1e-13 * scale
+
+
+def test_k1_ignores_upper_triangles():
+    from tests import gpu_util as G
+    n = 150
+    M = O.gen_sym(n, 9)
+    rng = np.random.default_rng(0)
+    va = rng.standard_normal(n) + 0j
+    vb = 1j * rng.standard_normal(n)
+    y0 = G.matvec(M, 0, va, vb)
+    M2 = M.copy()
+    iu = np.triu_indices(n, 1)
+    M2[:n, :n][iu] = np.nan
+    M2[n:, :n][iu] = np.nan
+    M2[n:, :n][np.diag_indices(n)] = np.nan
+    y1 = G.matvec(M2, 0, va, vb)
+    assert np.array_equal(y0[0], y1[0]) and np.array_equal(y0[1], y1[1])
+
+
+@pytest.mark.parametrize("ta,tb,M,N,Kd,lower", [(0, 1, 100, 100, 128, 1), (0, 1, 67, 67, 40, 1), (1, 0, 64, 130, 300, 0),
+                                                (0, 0, 200, 77, 64, 0), (0, 0, 5, 3, 2, 0), (1, 1, 33, 65, 17, 0),
+                                                (0, 1, 129, 129, 256, 0)])
+def test_zgemm(ta, tb, M, N, Kd, lower):
+    from tests import gpu_util as G
+    rng = np.random.default_rng(M * 7 + N)
+    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    A = cr(Kd, M) if ta else cr(M, Kd)
+    B = cr(N, Kd) if tb else cr(Kd, N)
+    C = cr(M, N)
+    alpha, beta = -1.0 + 0.5j, 1.0 - 0.25j
+    got, _ = G.zgemm(ta, tb, alpha, A, B, beta, C, lower)
+    opA = A.conj().T if ta else A
+    opB = B.conj().T if tb else B
+    ref = alpha * (opA @ opB) + beta * C
+    if lower:
+        ref = np.where(np.tril(np.ones((M, N), dtype=bool)), ref, C)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * Kd
+
+
+@pytest.mark.parametrize("name,d,e", list(_tri_cases()))
+def test_k8_stedc_cases(name, d, e):
+    from tests import gpu_util as G
+    rc, w, Z = G.stedc(d, e)
+    assert rc == 0
+    n = len(d)
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    wr = np.linalg.eigvalsh(Tm)
+    nrm = max(np.abs(wr).max(), 1e-300)
+    assert np.abs(w - wr).max() <= 50 * T.EPS * nrm
+    assert np.linalg.norm(Tm @ Z - Z * w) / (n * nrm * T.EPS) < 2.0
+    assert np.linalg.norm(Z.T @ Z - np.eye(n)) / (n * T.EPS) < 2.0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 64, 65, 100, 513, 1000, 2049])
+def test_k8_stedc_sizes(n):
+    from tests import gpu_util as G
+    rng = np.random.default_rng(n)
+    d = rng.standard_normal(n)
+    e = np.abs(rng.standard_normal(max(n - 1, 0)))
+    rc, w, Z = G.stedc(d, e)
+    assert rc == 0
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    wr = np.linalg.eigvalsh(Tm)
+    nrm = np.abs(wr).max()
+    assert np.abs(w - wr).max() <= 100 * T.EPS * nrm
+    assert np.linalg.norm(Tm @ Z - Z * w) / (n * nrm * T.EPS) < 2.0
+    assert np.linalg.norm(Z.T @ Z - np.eye(n)) / (n * T.EPS) < 2.0
+    assert np.all(np.diff(w) >= 0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 50, 333, 1500])
+def test_k9_bisect(n):
+    from tests import gpu_util as G
+    rng = np.random.default_rng(n)
+    d = rng.standard_normal(n)
+    e = rng.standard_normal(max(n - 1, 0))
+    w = G.bisect(d, e)
+    Tm = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    wr = np.linalg.eigvalsh(Tm)
+    assert np.abs(w - wr).max() <= 20 * T.EPS * max(np.abs(wr).max(), 1.0)
+
+
+@pytest.mark.parametrize("n,nb", [(2, 32), (3, 2), (21, 8), (22, 4), (64, 32), (65, 32), (130, 32), (200, 64), (300, 32)])
+def test_tridiagonalisation_vs_oracle(n, nb):
+    """K1-K4 chain == numpy restatement of the same formulation (different summation order only)."""
+    from tests import gpu_util as G
+    M = O.gen_sym(n, 200 + n)
+    d, e, tau, al, Ah = G.tridiag(M, nb)
+    dr, ala, alb, taur, Dr, Er = K.tridiagonalise(M[:n, :n], M[n:, :n], nb)
+    er = np.sqrt(np.abs(ala) ** 2 + np.abs(alb) ** 2)
+    nrm = np.linalg.norm(M, 2)
+    assert np.max(np.abs(d - dr)) <= 1e-12 * nrm
+    assert np.max(np.abs(e[: n - 1] - er)) <= 1e-12 * nrm
+    assert np.max(np.abs(tau[: n - 1] - taur)) <= 1e-10
+    # eigenvalues of the real tridiagonal == eigenvalues of M (each twice)
+    Tm = np.diag(d) + np.diag(e[: n - 1], 1) + np.diag(e[: n - 1], -1)
+    wm = np.linalg.eigvalsh(M)[0::2]
+    assert np.max(np.abs(np.linalg.eigvalsh(Tm) - wm)) <= 1e-12 * nrm
+    # reflector tails left in the lower triangles
+    low = np.tril_indices(n, -2)
+    assert np.max(np.abs(Ah[:n][low] - Dr[low])) <= 1e-10
+    assert np.max(np.abs(Ah[n:][low] - Er[low])) <= 1e-10

@@ -1,0 +1,208 @@
+"""-m gpu: parity of the full hot path (C ABI zquatev_b200 == ts::zquatev) with the reference:
+golden eigenvalues (tests/golden, generated from the unmodified reference), the reference library
+itself when oracle/_ref travelled to the box, the north_star quality metrics, and size-independent
+properties at sizes the CPU oracle cannot reach."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import zquatev_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TESTCC = json.load(open(os.path.join(GOLD, "testcc_eigs.json")))
+SYM = json.load(open(os.path.join(GOLD, "sym_eigs.json")))
+
+# north_star tolerance: eigenvalues within 1e-12 * ||A|| (2-norm of the matrix)
+EIG_TOL = 1e-12
+
+
+def check_quality(M, out, eig, g=None):
+    res, orth, pair = O.quality(M, out, eig)
+    assert pair == 0.0, "quaternion pairing must be exact"
+    if g is None:
+        assert res < 1.0 and orth < 2.0
+    else:   # at or below the reference's (15 % slack for run-to-run rounding noise, floors for tiny n)
+        assert res <= max(1.15 * g["residual"], 0.35), (res, g["residual"])
+        assert orth <= max(1.15 * g["orthogonality"], 1.2), (orth, g["orthogonality"])
+    return res, orth
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 21, 22, 23, 64, 200, 500])
+def test_testcc_golden(n):
+    """BASELINE config 1 family: the reference's own test matrix (test.cc:58-78)."""
+    from tests import gpu_util as G
+    _, _, C = O.gen_testcc(n)
+    eig, out, info = G.solve_host(C)
+    g = TESTCC[str(n)]
+    assert info == 0
+    assert np.all(eig[n:] == -777.0), "only n eigenvalues may be written (SURVEY A.1)"
+    assert np.max(np.abs(eig[:n] - np.array(g["eig"]))) <= EIG_TOL * g["two_norm"]
+    check_quality(C, out, eig[:n], g)
+    err, _ = O.testcc_checks(C, out, eig[:n])
+    assert err <= max(10 * g["testcc_error"], 1e-22)       # the number test.cc:114 prints
+
+
+@pytest.mark.parametrize("key", list(SYM))
+def test_sym_golden(key):
+    from tests import gpu_util as G
+    n, seed = (int(x) for x in key.split("_"))
+    M = O.gen_sym(n, seed)
+    eig, out, info = G.solve_host(M)
+    g = SYM[key]
+    assert info == 0
+    assert np.max(np.abs(eig[:n] - np.array(g["eig"]))) <= EIG_TOL * g["two_norm"]
+    check_quality(M, out, eig[:n], g)
+
+
+@pytest.mark.parametrize("nb", [1, 7, 20, 64])
+def test_panel_widths(nb):
+    from tests import gpu_util as G
+    n = 90
+    M = O.gen_sym(n, 5)
+    eig, out, info = G.solve_host(M, nb=nb)
+    wr = np.linalg.eigvalsh(M)[0::2]
+    assert info == 0 and np.max(np.abs(eig[:n] - wr)) <= EIG_TOL * np.abs(wr).max()
+    check_quality(M, out, eig[:n])
+
+
+@pytest.mark.skipif(not O.RefLib.available(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("n,seed", [(48, 1), (129, 2), (300, 3)])
+def test_against_reference_library(n, seed):
+    """identical random input through the unmodified reference (CPU) and the CUDA path; Kramers pairs
+    compared as 2-D subspaces (unit-quaternion gauge freedom)."""
+    from tests import gpu_util as G
+    ref = O.RefLib()
+    M = O.gen_sym(n, seed)
+    er, outr, ir = ref.zquatev(M)
+    eig, out, info = G.solve_host(M)
+    nrm = np.abs(er).max()
+    assert ir == 0 and info == 0
+    assert np.max(np.abs(eig[:n] - er)) <= EIG_TOL * nrm
+    rr, orr, _ = O.quality(M, outr, er)
+    res, orth, pair = O.quality(M, out, eig[:n])
+    assert pair == 0.0 and res <= max(1.15 * rr, 0.35) and orth <= max(1.15 * orr, 1.2)
+    gaps = np.minimum(np.diff(er, prepend=-np.inf), np.diff(er, append=np.inf))
+    for i in range(n):
+        if gaps[i] < 1e-6 * nrm:
+            continue
+        Pm = out[:, [i, i + n]]
+        Pr = outr[:, [i, i + n]]
+        sv = np.linalg.svd(Pr.conj().T @ Pm, compute_uv=False)
+        assert np.all(np.abs(sv - 1.0) <= 1e-9 * nrm / gaps[i]), (i, sv)
+
+
+def test_right_half_garbage_and_upper_triangles_ignored():
+    from tests import gpu_util as G
+    n = 40
+    M = O.gen_sym(n, 11)
+    e0, o0, _ = G.solve_host(M)
+    M2 = M.copy()
+    M2[:, n:] = np.nan                       # right half is never read (zquatev.h:45-46)
+    e1, o1, info = G.solve_host(M2)
+    assert info == 0 and np.array_equal(e0[:n], e1[:n]) and np.array_equal(o0, o1)
+
+
+def test_ld2_larger_than_n2():
+    """the reference is wrong for ld2 != n2; this build supports it."""
+    from tests import gpu_util as G
+    n = 33
+    M = O.gen_sym(n, 12)
+    e0, o0, _ = G.solve_host(M)
+    e1, o1, info = G.solve_host(M, ld2=2 * n + 6)
+    assert info == 0 and np.array_equal(e0[:n], e1[:n]) and np.array_equal(o0, o1)
+
+
+def test_nan_input_reports_info():
+    from tests import gpu_util as G
+    n = 30
+    M = O.gen_sym(n, 13)
+    M[5, 3] = np.nan
+    _, _, info = G.solve_host(M)
+    assert info > 0                           # reference: zhbev info > 0
+
+
+def test_diagonal_and_tridiagonal_inputs():
+    from tests import gpu_util as G
+    n = 50
+    lam = np.linspace(-1, 1, n)
+    M = O.assemble(np.diag(lam).astype(np.complex128), np.zeros((n, n), dtype=np.complex128))
+    eig, out, info = G.solve_host(M)
+    assert info == 0 and np.max(np.abs(eig[:n] - lam)) < 1e-14
+    check_quality(M, out, eig[:n])
+
+
+def test_clustered_spectrum():
+    from tests import gpu_util as G
+    n = 60
+    lam = np.array([1.0] * 20 + [2.0] * 10 + list(np.linspace(3, 4, 30)))
+    M = O.gen_spectrum(n, lam, 1)
+    eig, out, info = G.solve_host(M)
+    assert info == 0 and np.max(np.abs(eig[:n] - np.sort(lam))) <= 1e-13 * 4 * 10
+    check_quality(M, out, eig[:n])
+
+
+def test_values_only_and_bitwise_reproducible():
+    from tests import gpu_util as G
+    n = 150
+    M = O.gen_sym(n, 14)
+    e0, o0, _ = G.solve_host(M)
+    e1, o1, _ = G.solve_host(M)
+    assert np.array_equal(e0, e1) and np.array_equal(o0, o1)      # no atomics anywhere on the path
+    ev, _, info = G.solve_host(M, jobz=0)
+    assert info == 0 and np.max(np.abs(ev[:n] - e0[:n])) <= 1e-12 * np.abs(e0[:n]).max()
+
+
+def test_batched():
+    import zquatev_b200 as z
+    n, batch = 20, 5
+    Ms = [O.gen_sym(n, 1000 + b) for b in range(batch)]
+    D = np.stack([np.asfortranarray(M).T.copy() for M in Ms])     # each slab = column-major matrix
+    eig = np.zeros((batch, n))
+    info = z.zquatev_batched(D, eig)
+    assert np.all(info == 0)
+    for b in range(batch):
+        wr = np.linalg.eigvalsh(Ms[b])[0::2]
+        assert np.max(np.abs(eig[b] - wr)) <= 1e-12 * np.abs(wr).max()
+        out = D[b].T
+        assert O.quality(Ms[b], out, eig[b])[2] == 0.0
+
+
+@pytest.mark.parametrize("n", [1024, 2048])
+def test_properties_at_scale_device_resident(n):
+    """BASELINE config 2 family at sizes the CPU oracle cannot reach: size-independent properties,
+    computed on the device (torch is only the checker here): trace, sum of squares, residual,
+    orthogonality, exact pairing."""
+    import torch
+    import zquatev_b200 as z
+    g = torch.Generator(device="cuda").manual_seed(32)
+    X = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    Y = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    Dm = torch.complex(X, Y)
+    Dm = torch.tril(Dm, -1)
+    Dm = Dm + Dm.conj().T + torch.diag(torch.diagonal(X)).to(torch.complex128)
+    X2 = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    Y2 = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=g) - 0.5
+    Em = torch.tril(torch.complex(X2, Y2), -1)
+    Em = Em - Em.T
+    M = torch.cat([torch.cat([Dm, -Em.conj()], 1), torch.cat([Em, Dm.conj()], 1)], 0)   # M[row, col]
+    buf = M.T.contiguous()                     # column-major memory of M
+    buf[n:, :] = float("nan")                  # right half (columns n..) must not be read
+    eig = torch.zeros(n, dtype=torch.float64, device="cuda")
+    info = z.zquatev_device(2 * n, buf.data_ptr(), 2 * n, eig.data_ptr())
+    assert info == 0
+    V = buf.T                                  # (row, col) view of the result
+    lam = torch.cat([eig, eig])
+    eps = 2.220446049250313e-16
+    N = 2 * n
+    nrmM = torch.linalg.norm(M)
+    res = torch.linalg.norm(M @ V - V * lam[None, :]) / (N * nrmM * eps)
+    orth = torch.linalg.norm(V.conj().T @ V - torch.eye(N, dtype=torch.complex128, device="cuda")) / (N * eps)
+    assert abs(eig.sum().item() - torch.diagonal(Dm).real.sum().item()) <= 1e-10 * n
+    assert abs((eig ** 2).sum().item() - 0.5 * (nrmM ** 2).item()) <= 1e-10 * (nrmM ** 2).item()
+    assert res.item() < 0.5 and orth.item() < 1.5, (res.item(), orth.item())
+    U, W = V[:n, :n], V[n:, :n]
+    assert torch.equal(V[:n, n:], -W.conj()) and torch.equal(V[n:, n:], U.conj())
+    assert bool(torch.all(eig[1:] >= eig[:-1]))

@@ -1,0 +1,88 @@
+// Host-callable launchers of the zquatev B200 kernels (all asynchronous on `st`).
+// Kernel ids K1..K10 follow SURVEY.md 7.2 / DESIGN.md.
+#pragma once
+#include "common.cuh"
+
+namespace zq {
+
+// ---- geometry of the K1 tiles (shared by matvec.cu and panel.cu) ----
+constexpr int MV_TR = 128;   // tile rows  (4 rows per lane)
+constexpr int MV_TC = 64;    // tile cols  (8 warps x 8 columns)
+constexpr int DOT_ROWS = 512;
+constexpr int ROWS_PER_CTA = 256;
+
+struct PanelWs {
+  int n, nb;
+  size_t lda;         // leading dimension of A (complex elements)
+  cplx* A;            // 2n x n: D rows [0,n), E rows [n,2n)
+  cplx* pan;          // [4][nb][n]: Va, Vb, Wa, Wb
+  quat* x;            // [n] current (updated) column
+  quat* vq;           // [n] current reflector, zero outside its support
+  quat* p;            // [n] tau * (M v - corrections)
+  quat* pd;           // [ceil(n/MV_TC)][n]  direct partial sums of K1
+  quat* pt;           // [ceil(n/MV_TR)][n]  transposed partial sums of K1
+  quat* dotW;         // [nchunks][nb]  partial W^H v
+  quat* dotV;         // [nchunks][nb]  partial V^H v
+  double* nrm_part;   // [ceil(n/256)]
+  double* g_part;     // [ceil(n/256)]
+  double* d;          // [n]   diagonal of the real tridiagonal
+  double* e;          // [n]   |alpha_k|
+  double* tau;        // [n]
+  quat* alpha;        // [n]   quaternion sub-diagonal
+  quat* G;            // [n][nb] saved V^H v_i (strict upper part of the panel Gram matrix)
+};
+
+// K2/K3 panel column kernels (panel.cu)
+void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st);
+void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st);
+void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
+void launch_finish_w(const PanelWs& w, int k_last, int j0, cudaStream_t st);
+// K1 quaternion-Hermitian mat-vec on the lower triangles (+ fused panel dot products)
+void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st);
+// stand-alone K1 for tests/bench: y = M[s:,s:] v (rows < s of v must be zero)
+void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st);
+
+// K4 operands: L (2m x 4kb, ld 2m) and R (m x 4kb, ld m) from the panel, m = n - r0
+void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStream_t st);
+
+// K4/K6 complex GEMM:  C = alpha * op(A) * op(B) + beta * C
+//   ta/tb: 0 = as stored, 1 = conjugate transpose.  lower != 0: only tiles with row >= col are
+//   computed and, inside diagonal tiles, only entries with row >= col are stored.
+//   Batched over `batch` with element strides sA, sB, sC.
+void launch_zgemm(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
+                  size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
+                  size_t sC, cudaStream_t st);
+
+// K6 helpers (backtransform.cu)
+//   P = Phi(V) of panel [j0, j0+kb): (2m x 2kb), ld 2m, m = n-1-j0 ; rows [0,m) <-> a-part rows j0+1..
+void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st);
+//   T (2kb x 2kb complex, ld 2kb) from saved Gram columns G and tau
+void launch_build_T(const PanelWs& w, int j0, int kb, cplx* T, cudaStream_t st);
+//   phase chain s (n quats) from alpha; X0 = diag(s) Z[:, perm]
+void launch_phase_chain(int n, const quat* alpha, const double* e, quat* s, cudaStream_t st);
+void launch_scale_Z(int n, const double* Z, size_t ldz, const int* perm, const quat* s, cplx* X, size_t ldx,
+                    cudaStream_t st);
+// K10 pairing: right half = Theta(left half)
+void launch_pairing(int n, cplx* Out, size_t ld, cudaStream_t st);
+// in-place variant used by the driver: X sits in the RIGHT half (columns n..2n-1); on exit the left
+// half holds (U;V) = X and the right half Theta(X) = (-conj V; conj U)
+void launch_swap_pairing(int n, cplx* Out, size_t ld, cudaStream_t st);
+
+// K8 tridiagonal divide & conquer (dc.cu).  d,e: n ; Z: n x n (ldz) ; on exit w ascending = d[perm[.]]
+struct DcWs;
+DcWs* dc_create(int n);
+void dc_destroy(DcWs*);
+size_t dc_bytes(int n);
+// returns 0 / cuda error; eigenvalues (ascending) -> wout[n]; eigenvectors: column j of the result is
+// column perm[j] of Zres (pointer returned in *Zres, ld n).  info flag on device: *info_dev != 0 -> failure.
+int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, double** Zres, int** perm,
+             int* info_dev, cudaStream_t st);
+
+// K9 eigenvalues only: Sturm bisection
+// scratch: n + 3 doubles
+void launch_bisect(int n, const double* d, const double* e, double* w, double* scratch, cudaStream_t st);
+
+// misc
+void launch_check_finite(int n, const double* d, const double* e, int* flag, cudaStream_t st);
+
+}  // namespace zq

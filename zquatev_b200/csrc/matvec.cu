@@ -1,0 +1,189 @@
+// K1: quaternion-Hermitian matrix-vector product on the LOWER triangles,
+//       y = (D + jE) v  restricted to rows/cols [s, n),
+// the HBM-bound kernel of the tridiagonalisation.  It replaces the four zgemv passes per
+// column of the reference (blocked.cc:214,219,397,402 -- each streams the trailing D0 or D1
+// once) by ONE pass over the lower triangles of D and E: 16*m^2 bytes per column instead of
+// the reference's 64*m^2.
+//
+// Tile = 128 rows x 64 columns, one CTA of 8 warps.  Warp w owns 8 columns of the tile, lane l
+// owns rows l, l+32, l+64, l+96, so every load instruction of a warp reads 512 contiguous bytes
+// (32 consecutive complex<double> of one column).  Each loaded pair (d,e) = (D[r,c], E[r,c])
+// feeds both the direct product (row r, accumulated in registers over the warp's columns) and
+// the transposed product (column c, accumulated over the lane's 4 rows and then reduced with
+// warp shuffles).  Direct partials are summed across the 8 warps through shared memory and
+// written to pd[J][r]; transposed sums go to pt[I][c]; reduce_correct (panel.cu) adds them in
+// a fixed order -> bit-reproducible, no atomics.
+//
+// The same launch carries extra CTAs that compute the partial panel inner products
+// W^H v and V^H v (skinny GEMV^H over rows [s, n)), which the correction step needs.
+#include "kernels.h"
+
+namespace zq {
+namespace {
+
+constexpr int TR = MV_TR, TC = MV_TC, RI = TR / 32, NW = 8, CW = TC / NW;
+
+struct TileIdx { int I, J; };
+
+ZQ_D TileIdx decode_tile(int t, int s, int n) {
+  const int I0 = s / TR, J0 = s / TC, Jlast = (n - 1) / TC;
+  int I = I0;
+  for (;;) {
+    const int cnt = min(2 * I + 1, Jlast) - J0 + 1;
+    if (t < cnt) break;
+    t -= cnt;
+    ++I;
+  }
+  TileIdx ti; ti.I = I; ti.J = J0 + t;
+  return ti;
+}
+
+inline int count_tiles(int s, int n) {
+  const int I0 = s / TR, I1 = (n - 1) / TR, J0 = s / TC, Jlast = (n - 1) / TC;
+  int tot = 0;
+  for (int I = I0; I <= I1; ++I) tot += (2 * I + 1 < Jlast ? 2 * I + 1 : Jlast) - J0 + 1;
+  return tot;
+}
+
+template <bool FULL>
+ZQ_D void tile_body(const cplx* __restrict__ A, size_t lda, int n, int r0, int c0, const quat (&vrow)[RI],
+                    const quat* vcol, quat (&acc)[RI], quat* pt_row, int lane, int warp) {
+  const cplx* Dp = A + (size_t)r0 + lane;
+  const cplx* Ep = Dp + n;
+#pragma unroll 2
+  for (int jj = 0; jj < CW; ++jj) {
+    const int c = c0 + warp * CW + jj;
+    cplx dv[RI], ev[RI];
+    if (FULL) {
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        dv[i] = ld_stream(Dp + (size_t)c * lda + 32 * i);
+        ev[i] = ld_stream(Ep + (size_t)c * lda + 32 * i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        const int r = r0 + lane + 32 * i;
+        const bool ok = (r < n) && (c < n) && (r >= c);
+        dv[i] = ok ? ld_stream(Dp + (size_t)c * lda + 32 * i) : cmake(0, 0);
+        ev[i] = (ok && r > c) ? ld_stream(Ep + (size_t)c * lda + 32 * i) : cmake(0, 0);
+      }
+    }
+    const quat vc = vcol[warp * CW + jj];
+    quat tacc = qzero();
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+      cplx d = dv[i];
+      const cplx e = ev[i];
+      if (!FULL) {
+        const int r = r0 + lane + 32 * i;
+        if (r == c) {                       // diagonal: D real, E zero; direct term only
+          acc[i].a.x = fma(d.x, vc.a.x, acc[i].a.x); acc[i].a.y = fma(d.x, vc.a.y, acc[i].a.y);
+          acc[i].b.x = fma(d.x, vc.b.x, acc[i].b.x); acc[i].b.y = fma(d.x, vc.b.y, acc[i].b.y);
+          d = cmake(0, 0);
+        }
+      }
+      // direct: ya[r] += d va[c] - conj(e) vb[c] ; yb[r] += e va[c] + conj(d) vb[c]
+      cfma(acc[i].a, d, vc.a);  cfms_ca(acc[i].a, e, vc.b);
+      cfma(acc[i].b, e, vc.a);  cfma_ca(acc[i].b, d, vc.b);
+      // transposed: ya[c] += conj(d) va[r] + conj(e) vb[r] ; yb[c] += -e va[r] + d vb[r]
+      cfma_ca(tacc.a, d, vrow[i].a);  cfma_ca(tacc.a, e, vrow[i].b);
+      cfms(tacc.b, e, vrow[i].a);     cfma(tacc.b, d, vrow[i].b);
+    }
+    tacc = warp_sum(tacc);
+    if (lane == 0 && c < n) pt_row[c] = tacc;
+  }
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __restrict__ vq, quat* __restrict__ pd,
+         quat* __restrict__ pt, int ntiles,
+         // fused panel dots
+         const cplx* __restrict__ pan, int nb, int ncols, quat* __restrict__ dotW, quat* __restrict__ dotV) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x >= ntiles) {
+    // ---- panel inner products: chunk of DOT_ROWS rows, warp per column t ----
+    const int ch = blockIdx.x - ntiles;
+    const int ra = s + ch * DOT_ROWS, rb = min(n, ra + DOT_ROWS);
+    for (int t = warp; t < ncols; t += NW) {
+      const cplx* va = pan + ((size_t)(0 * nb + t)) * n;
+      const cplx* vb = pan + ((size_t)(1 * nb + t)) * n;
+      const cplx* wa = pan + ((size_t)(2 * nb + t)) * n;
+      const cplx* wb = pan + ((size_t)(3 * nb + t)) * n;
+      quat aW = qzero(), aV = qzero();
+      for (int r = ra + lane; r < rb; r += 32) {
+        const quat f = vq[r];
+        qfma_cj(aW, qmake(wa[r], wb[r]), f);
+        qfma_cj(aV, qmake(va[r], vb[r]), f);
+      }
+      aW = warp_sum(aW);
+      aV = warp_sum(aV);
+      if (lane == 0) {
+        dotW[(size_t)ch * nb + t] = aW;
+        dotV[(size_t)ch * nb + t] = aV;
+      }
+    }
+    return;
+  }
+  __shared__ quat vcol[TC];
+  __shared__ quat red[NW][TR];
+  const TileIdx ti = decode_tile(blockIdx.x, s, n);
+  const int r0 = ti.I * TR, c0 = ti.J * TC;
+  if (threadIdx.x < TC) {
+    const int c = c0 + threadIdx.x;
+    vcol[threadIdx.x] = (c < n) ? vq[c] : qzero();
+  }
+  quat vrow[RI], acc[RI];
+#pragma unroll
+  for (int i = 0; i < RI; ++i) {
+    const int r = r0 + lane + 32 * i;
+    vrow[i] = (r < n) ? vq[r] : qzero();
+    acc[i] = qzero();
+  }
+  __syncthreads();
+  const bool full = (c0 + TC - 1 < r0) && (r0 + TR <= n);
+  quat* pt_row = pt + (size_t)ti.I * n;
+  if (full) tile_body<true>(A, lda, n, r0, c0, vrow, vcol, acc, pt_row, lane, warp);
+  else      tile_body<false>(A, lda, n, r0, c0, vrow, vcol, acc, pt_row, lane, warp);
+#pragma unroll
+  for (int i = 0; i < RI; ++i) red[warp][lane + 32 * i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < TR) {
+    const int r = r0 + threadIdx.x;
+    quat sum = red[0][threadIdx.x];
+#pragma unroll
+    for (int wv = 1; wv < NW; ++wv) sum = qadd(sum, red[wv][threadIdx.x]);
+    if (r < n) pd[(size_t)ti.J * n + r] = sum;
+  }
+}
+
+// y[r] = sum of partials, rows [s, n) -- only used by the stand-alone test/bench entry
+__global__ void k_matvec_gather(int n, int s, const quat* pd, const quat* pt, quat* y) {
+  const int r = s + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int J0 = s / TC, Jlast = (n - 1) / TC, I0 = s / TR, I1 = (n - 1) / TR;
+  const int Jhi = min(2 * (r / TR) + 1, Jlast), Ilo = max(I0, (r / TC) / 2);
+  quat acc = qzero();
+  for (int J = J0; J <= Jhi; ++J) acc = qadd(acc, pd[(size_t)J * n + r]);
+  for (int I = Ilo; I <= I1; ++I) acc = qadd(acc, pt[(size_t)I * n + r]);
+  y[r] = acc;
+}
+
+}  // namespace
+
+void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
+  const int s = k + 1, n = w.n;
+  const int ntiles = count_tiles(s, n);
+  const int ncols = k - j0;
+  const int nch = ncols > 0 ? (n - s + DOT_ROWS - 1) / DOT_ROWS : 0;
+  k_matvec<<<ntiles + nch, 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, ntiles, w.pan, w.nb, ncols, w.dotW, w.dotV);
+}
+
+void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st) {
+  const int n = w.n;
+  const int ntiles = count_tiles(s, n);
+  k_matvec<<<ntiles, 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, ntiles, w.pan, w.nb, 0, w.dotW, w.dotV);
+  k_matvec_gather<<<(n - s + 255) / 256, 256, 0, st>>>(n, s, w.pd, w.pt, y);
+}
+
+}  // namespace zq

@@ -1,0 +1,248 @@
+// K2/K3: panel column kernels of the quaternion Householder tridiagonalisation.
+//
+// Replaces the k-loop of ts::impl::panel_update (reference blocked.cc:70-414: lazy column
+// update :73-164, zlarfg :176/:345, zlartg :237, growth of T/R/S/W/Y/Z :171-413) with ONE
+// quaternion reflector per column.  Per column k = j0 + i:
+//   col_update      x = M[:,k] - V W[k,:]^* - W V[k,:]^*   (and finishes w of column k-1)
+//   reflector       v, tau, alpha from x  (zlarfg analogue, tau real)
+//   matvec (K1)     partial sums of M v   + partial W^H v, V^H v
+//   reduce_correct  p = tau (M v - V (W^H v) - W (V^H v)),  partial Re(v^H p)
+// All cross-CTA reductions go through small partial buffers summed in a fixed order, so the
+// result is bit-reproducible run to run.
+#include "kernels.h"
+
+namespace zq {
+
+namespace {
+
+constexpr int NT = ROWS_PER_CTA;
+
+ZQ_D cplx* pan_ptr(const PanelWs& w, int which, int t) { return w.pan + ((size_t)(which * w.nb + t)) * w.n; }
+
+// ---------------------------------------------------------------------------------------------
+// col_update: rows r in [k, n)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int ng_parts) {
+  const int n = w.n, i = k - j0;
+  const int r = k + blockIdx.x * NT + threadIdx.x;
+  __shared__ quat qW[128], qV[128];
+  __shared__ double s_red[32];
+  const bool act = r < n;
+
+  quat wr = qzero();       // W(r, i-1) for this thread's row
+  if (i > 0) {
+    // finish w of the previous column: w = p - 1/2 tau (v^H p) v   (zlatrd-style; tau real)
+    double g = 0.0;
+    for (int j = 0; j < ng_parts; ++j) g += w.g_part[j];
+    const double coef = 0.5 * w.tau[k - 1] * g;
+    const cplx* va = pan_ptr(w, 0, i - 1);
+    const cplx* vb = pan_ptr(w, 1, i - 1);
+    if (act) {
+      quat pr = w.p[r];
+      quat vr = qmake(va[r], vb[r]);
+      wr = qmake(csub(pr.a, cscale(vr.a, coef)), csub(pr.b, cscale(vr.b, coef)));
+      pan_ptr(w, 2, i - 1)[r] = wr.a;
+      pan_ptr(w, 3, i - 1)[r] = wr.b;
+    }
+    // row-k coefficients: qconj(W(k,t)), qconj(V(k,t)), t < i
+    for (int t = threadIdx.x; t < i; t += NT) {
+      quat wk, vk;
+      if (t == i - 1) {
+        quat pk = w.p[k];
+        quat vkk = qmake(va[k], vb[k]);
+        wk = qmake(csub(pk.a, cscale(vkk.a, coef)), csub(pk.b, cscale(vkk.b, coef)));
+        vk = vkk;
+      } else {
+        wk = qmake(pan_ptr(w, 2, t)[k], pan_ptr(w, 3, t)[k]);
+        vk = qmake(pan_ptr(w, 0, t)[k], pan_ptr(w, 1, t)[k]);
+      }
+      qW[t] = qconj(wk);
+      qV[t] = qconj(vk);
+    }
+  }
+  __syncthreads();
+
+  double nr = 0.0;
+  if (act) {
+    quat col = qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]);
+    for (int t = 0; t < i; ++t) {
+      quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
+      quat wrt = (t == i - 1) ? wr : qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
+      qfms(col, vrt, qW[t]);
+      qfms(col, wrt, qV[t]);
+    }
+    if (r == k) {
+      w.d[k] = col.a.x;
+    } else {
+      w.x[r] = col;
+      if (r >= k + 2) nr = qnorm2(col);
+    }
+  }
+  double v1[1] = {nr};
+  block_sum<1>(v1, s_red);
+  if (threadIdx.x == 0) w.nrm_part[blockIdx.x] = v1[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// reflector: rows r in [k+1, n)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_reflector(PanelWs w, int k, int j0, int nparts) {
+  const int n = w.n, i = k - j0;
+  const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
+  double rest2 = 0.0;
+  for (int j = 0; j < nparts; ++j) rest2 += w.nrm_part[j];
+  const quat x1 = w.x[k + 1];
+  const double x1n2 = qnorm2(x1);
+  const double nx2 = rest2 + x1n2;
+  quat alpha = qzero(), inv = qzero();
+  double tau = 0.0, nx = 0.0;
+  if (nx2 > 0.0) {
+    nx = sqrt(nx2);
+    const double x1n = sqrt(x1n2);
+    quat ph = (x1n > 0.0) ? qscale(x1, 1.0 / x1n) : qmake(cmake(1, 0), cmake(0, 0));
+    alpha = qscale(ph, -nx);
+    const double u1n = x1n + nx;                 // u1 = x1 - alpha = phase * (|x1| + ||x||)
+    const double u1n2 = u1n * u1n;
+    tau = 2.0 * u1n2 / (rest2 + u1n2);
+    inv = qscale(qconj(ph), 1.0 / u1n);          // u1^{-1}
+  }
+  if (r < n) {
+    quat v;
+    if (r == k + 1) {
+      v = qmake(cmake(1, 0), cmake(0, 0));
+      w.vq[k] = qzero();
+    } else {
+      v = qmul(w.x[r], inv);                     // right scaling keeps H = I - tau v v^H Hermitian
+      w.A[(size_t)r + (size_t)k * w.lda] = v.a;  // reflector tail lives where zeros were created
+      w.A[(size_t)(n + r) + (size_t)k * w.lda] = v.b;
+    }
+    pan_ptr(w, 0, i)[r] = v.a;
+    pan_ptr(w, 1, i)[r] = v.b;
+    w.vq[r] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    w.alpha[k] = alpha;
+    w.e[k] = nx;
+    w.tau[k] = tau;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduce_correct: rows r in [k+1, n)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0, int nch) {
+  const int n = w.n, i = k - j0, s = k + 1;
+  const int r = s + blockIdx.x * NT + threadIdx.x;
+  __shared__ quat gW[128], gV[128];
+  __shared__ double s_red[32];
+  for (int t = threadIdx.x; t < 2 * i; t += NT) {
+    const int tt = t >> 1;
+    const quat* src = (t & 1) ? w.dotV : w.dotW;
+    quat acc = qzero();
+    for (int c = 0; c < nch; ++c) acc = qadd(acc, src[(size_t)c * w.nb + tt]);
+    if (t & 1) gV[tt] = acc; else gW[tt] = acc;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    for (int t = threadIdx.x; t < i; t += NT) w.G[(size_t)k * w.nb + t] = gV[t];
+  }
+  double g = 0.0;
+  if (r < n) {
+    const int J0 = s / MV_TC, Jlast = (n - 1) / MV_TC;
+    const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
+    const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
+    const int Ilo = max(I0, (r / MV_TC) / 2);
+    quat y = qzero();
+    for (int J = J0; J <= Jhi; ++J) y = qadd(y, w.pd[(size_t)J * n + r]);
+    for (int I = Ilo; I <= I1; ++I) y = qadd(y, w.pt[(size_t)I * n + r]);
+    for (int t = 0; t < i; ++t) {
+      quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
+      quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
+      qfms(y, vrt, gW[t]);
+      qfms(y, wrt, gV[t]);
+    }
+    const double tau = w.tau[k];
+    y = qscale(y, tau);
+    w.p[r] = y;
+    const quat f = w.vq[r];
+    g = f.a.x * y.a.x + f.a.y * y.a.y + f.b.x * y.b.x + f.b.y * y.b.y;   // Re(f^H y)
+  }
+  double v1[1] = {g};
+  block_sum<1>(v1, s_red);
+  if (threadIdx.x == 0) w.g_part[blockIdx.x] = v1[0];
+}
+
+// finish w of the LAST column of a panel (col_update does it for the others)
+__global__ void __launch_bounds__(NT) k_finish_w(PanelWs w, int k, int j0, int ng_parts) {
+  const int n = w.n, i = k - j0;
+  const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
+  double g = 0.0;
+  for (int j = 0; j < ng_parts; ++j) g += w.g_part[j];
+  const double coef = 0.5 * w.tau[k] * g;
+  if (r < n) {
+    quat pr = w.p[r];
+    quat vr = qmake(pan_ptr(w, 0, i)[r], pan_ptr(w, 1, i)[r]);
+    pan_ptr(w, 2, i)[r] = csub(pr.a, cscale(vr.a, coef));
+    pan_ptr(w, 3, i)[r] = csub(pr.b, cscale(vr.b, coef));
+  }
+}
+
+// K4 operand staging: L = [[Va, conj Vb, Wa, conj Wb], [Vb, -conj Va, Wb, -conj Wa]],
+//                     R = [Wa, conj Wb, Va, conj Vb]   (rows r0..n-1)
+__global__ void __launch_bounds__(256) k_build_LR(PanelWs w, int r0, int kb, cplx* L, cplx* R) {
+  const int n = w.n, m = n - r0;
+  const int t = blockIdx.y;
+  const int rr = blockIdx.x * 256 + threadIdx.x;
+  if (rr >= m) return;
+  const int r = r0 + rr;
+  const cplx va = pan_ptr(w, 0, t)[r], vb = pan_ptr(w, 1, t)[r];
+  const cplx wa = pan_ptr(w, 2, t)[r], wb = pan_ptr(w, 3, t)[r];
+  const size_t ldl = 2 * (size_t)m, ldr = m;
+  L[rr + (size_t)(0 * kb + t) * ldl] = va;
+  L[rr + (size_t)(1 * kb + t) * ldl] = cconj(vb);
+  L[rr + (size_t)(2 * kb + t) * ldl] = wa;
+  L[rr + (size_t)(3 * kb + t) * ldl] = cconj(wb);
+  L[m + rr + (size_t)(0 * kb + t) * ldl] = vb;
+  L[m + rr + (size_t)(1 * kb + t) * ldl] = cneg(cconj(va));
+  L[m + rr + (size_t)(2 * kb + t) * ldl] = wb;
+  L[m + rr + (size_t)(3 * kb + t) * ldl] = cneg(cconj(wa));
+  R[rr + (size_t)(0 * kb + t) * ldr] = wa;
+  R[rr + (size_t)(1 * kb + t) * ldr] = cconj(wb);
+  R[rr + (size_t)(2 * kb + t) * ldr] = va;
+  R[rr + (size_t)(3 * kb + t) * ldr] = cconj(vb);
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st) {
+  const int rows = w.n - k;                    // rows k..n-1
+  const int ng = (k > j0) ? cdiv(w.n - k, NT) : 0;   // g_part written by reduce_correct of column k-1 (rows k..n-1)
+  k_col_update<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, ng);
+}
+
+void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  const int nparts = cdiv(w.n - k, NT);        // nrm_part written by col_update (rows k..n-1)
+  k_reflector<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, nparts);
+}
+
+void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  const int nch = cdiv(rows, DOT_ROWS);
+  k_reduce_correct<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, nch);
+}
+
+void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  k_finish_w<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, cdiv(rows, NT));
+}
+
+void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStream_t st) {
+  const int m = w.n - r0;
+  dim3 g(cdiv(m, 256), kb);
+  k_build_LR<<<g, 256, 0, st>>>(w, r0, kb, L, R);
+}
+
+}  // namespace zq

@@ -1,0 +1,454 @@
+// Host orchestrator + C ABI (include/zquatev_b200.h).
+//
+// Mirrors the driver of the reference, ts::zquatev (zquatev.cc:42-100):
+//   reference                                   here
+//   repack D0/D1, Q0=I, Q1=0   (:48-61)         none: kernels index (A;B) in place; Q never formed
+//   panel_update / unblocked   (:68-72)         tridiagonalise(): col_update, reflector, K1, reduce_correct, K4
+//   band pack + zhbev          (:76-84)         phase chain + dc_solve() (K8) or bisection (K9)
+//   U = Q0 Z, V = Q1 Z         (:87-90)         backtransform(): compact-WY GEMMs on X0 = diag(s) Z (K6)
+//   symmetry fill              (:93-98)         swap_pairing (K10)
+// Everything is enqueued on one stream; the host never waits inside a solve except for the
+// final status word.
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "kernels.h"
+#include "../../include/zquatev_b200.h"
+
+int zq_cuda_fail(cudaError_t e, const char* file, int line) {
+  fprintf(stderr, "[zquatev_b200] CUDA error %d (%s) at %s:%d\n", (int)e, cudaGetErrorString(e), file, line);
+  return -(1000 + (int)e);
+}
+
+namespace zq {
+
+constexpr int DEFAULT_NB = 32;
+constexpr int MAX_NB = 64;
+
+struct Plan {
+  int n = 0, nb = 0, device = -1;
+  char* slab = nullptr;
+  PanelWs pw{};
+  cplx *L = nullptr, *R = nullptr, *P = nullptr, *T = nullptr, *Y = nullptr, *TY = nullptr;
+  quat* s = nullptr;
+  double* bis = nullptr;
+  int* info_dev = nullptr;
+  DcWs* dc = nullptr;
+  cplx* Dfull = nullptr;     // host-pointer mode staging, 2n x 2n
+  double* eig_dev = nullptr;
+  cudaEvent_t ev[6] = {};
+  std::vector<cudaEvent_t> k1ev;
+  double phase_ms[8] = {};
+  long launches = 0;
+};
+
+static std::mutex g_mu;
+static Plan* g_plan = nullptr;
+static bool g_profile = false;
+
+static void plan_free(Plan* p) {
+  if (!p) return;
+  if (p->slab) cudaFree(p->slab);
+  if (p->Dfull) cudaFree(p->Dfull);
+  if (p->dc) dc_destroy(p->dc);
+  for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : p->k1ev) cudaEventDestroy(e);
+  delete p;
+}
+
+static int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+static int plan_create(int n, int nb, Plan** out) {
+  Plan* p = new Plan();
+  p->n = n;
+  p->nb = nb;
+  cudaError_t e0 = cudaGetDevice(&p->device);
+  if (e0 != cudaSuccess) { delete p; return zq_cuda_fail(e0, __FILE__, __LINE__); }
+  const size_t N = (size_t)n;
+  size_t bytes = 0;
+  auto take = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
+  const size_t o_pan = take(4 * (size_t)nb * N * sizeof(cplx));
+  const size_t o_x = take(N * sizeof(quat)), o_vq = take(N * sizeof(quat)), o_p = take(N * sizeof(quat));
+  const size_t o_pd = take((size_t)cdiv(n, MV_TC) * N * sizeof(quat));
+  const size_t o_pt = take((size_t)cdiv(n, MV_TR) * N * sizeof(quat));
+  const size_t nch = (size_t)cdiv(n, DOT_ROWS) + 1;
+  const size_t o_dW = take(nch * nb * sizeof(quat)), o_dV = take(nch * nb * sizeof(quat));
+  const size_t nparts = (size_t)cdiv(n, ROWS_PER_CTA) + 1;
+  const size_t o_np = take(nparts * 8), o_gp = take(nparts * 8);
+  const size_t o_d = take(N * 8), o_e = take(N * 8), o_tau = take(N * 8), o_al = take(N * sizeof(quat));
+  const size_t o_G = take(N * nb * sizeof(quat));
+  const size_t o_L = take(2 * N * 4 * nb * sizeof(cplx)), o_R = take(N * 4 * nb * sizeof(cplx));
+  const size_t o_P = take(2 * N * 2 * nb * sizeof(cplx)), o_T = take((size_t)4 * nb * nb * sizeof(cplx));
+  const size_t o_Y = take((size_t)2 * nb * N * sizeof(cplx)), o_TY = take((size_t)2 * nb * N * sizeof(cplx));
+  const size_t o_s = take(N * sizeof(quat)), o_bis = take((N + 8) * 8), o_info = take(256), o_eig = take(N * 8);
+  cudaError_t e = cudaMalloc(&p->slab, bytes);
+  if (e != cudaSuccess) { delete p; return zq_cuda_fail(e, __FILE__, __LINE__); }
+  char* b = p->slab;
+  PanelWs& w = p->pw;
+  w.n = n; w.nb = nb; w.lda = 0; w.A = nullptr;
+  w.pan = (cplx*)(b + o_pan); w.x = (quat*)(b + o_x); w.vq = (quat*)(b + o_vq); w.p = (quat*)(b + o_p);
+  w.pd = (quat*)(b + o_pd); w.pt = (quat*)(b + o_pt); w.dotW = (quat*)(b + o_dW); w.dotV = (quat*)(b + o_dV);
+  w.nrm_part = (double*)(b + o_np); w.g_part = (double*)(b + o_gp);
+  w.d = (double*)(b + o_d); w.e = (double*)(b + o_e); w.tau = (double*)(b + o_tau); w.alpha = (quat*)(b + o_al);
+  w.G = (quat*)(b + o_G);
+  p->L = (cplx*)(b + o_L); p->R = (cplx*)(b + o_R); p->P = (cplx*)(b + o_P); p->T = (cplx*)(b + o_T);
+  p->Y = (cplx*)(b + o_Y); p->TY = (cplx*)(b + o_TY); p->s = (quat*)(b + o_s); p->bis = (double*)(b + o_bis);
+  p->info_dev = (int*)(b + o_info); p->eig_dev = (double*)(b + o_eig);
+  for (auto& ev : p->ev) cudaEventCreate(&ev);
+  *out = p;
+  return 0;
+}
+
+static int get_plan(int n, int nb, Plan** out) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return zq_cuda_fail(e, __FILE__, __LINE__);
+  if (g_plan && g_plan->n == n && g_plan->nb == nb && g_plan->device == dev) { *out = g_plan; return 0; }
+  if (g_plan) { cudaDeviceSynchronize(); plan_free(g_plan); g_plan = nullptr; }
+  int rc = plan_create(n, nb, &g_plan);
+  *out = g_plan;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1-K4: reduction of (D; E) to a quaternion tridiagonal, reflectors left in the lower triangles
+// ---------------------------------------------------------------------------------------------
+static void tridiagonalise(Plan* p, cudaStream_t st) {
+  const PanelWs& w = p->pw;
+  const int n = w.n, nb = w.nb;
+  cudaMemsetAsync(w.vq, 0, (size_t)n * sizeof(quat), st);
+  cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
+  cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
+  cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
+  const bool prof = g_profile;
+  if (prof && p->k1ev.size() < 2 * (size_t)n) {
+    const size_t old = p->k1ev.size();
+    p->k1ev.resize(2 * (size_t)n);
+    for (size_t i = old; i < p->k1ev.size(); ++i) cudaEventCreate(&p->k1ev[i]);
+  }
+  for (int j0 = 0; j0 < n - 1; j0 += nb) {
+    const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
+    for (int i = 0; i < kb; ++i) {
+      const int k = j0 + i;
+      launch_col_update(w, k, j0, st);
+      launch_reflector(w, k, j0, st);
+      if (prof) cudaEventRecord(p->k1ev[2 * k], st);
+      launch_matvec(w, k, j0, st);
+      if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
+      launch_reduce_correct(w, k, j0, st);
+      p->launches += 4;
+    }
+    launch_finish_w(w, j0 + kb - 1, j0, st);
+    const int r0 = j0 + kb, m = n - r0;
+    if (m > 0) {
+      launch_build_LR(w, r0, kb, p->L, p->R, st);
+      // [D;E][r0:, r0:] -= L R^H on the lower triangles: batch 0 = D block, batch 1 = E block
+      launch_zgemm(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
+                   w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, st);
+      p->launches += 3;
+    }
+  }
+  launch_col_update(w, n - 1, n - 1, st);   // d[n-1]
+  p->launches += 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: X <- H_0 ... H_{n-2} X, X = stacked (Xa; Xb), 2n x n, leading dimension ldx
+// ---------------------------------------------------------------------------------------------
+static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t st) {
+  const PanelWs& w = p->pw;
+  const int n = w.n, nb = w.nb;
+  if (n < 2) return;
+  const int last = ((n - 2) / nb) * nb;
+  for (int j0 = last; j0 >= 0; j0 -= nb) {
+    const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
+    const int m = n - 1 - j0;
+    launch_build_phi(w, j0, kb, p->P, st);
+    launch_build_T(w, j0, kb, p->T, st);
+    const size_t ldp = 2 * (size_t)m;
+    cplx* Xa = X + (size_t)(j0 + 1);
+    cplx* Xb = X + (size_t)(n + j0 + 1);
+    // Y = P^H X   (two K segments: a-rows and b-rows)
+    launch_zgemm(1, 0, 2 * kb, ncols, m, cmake(1, 0), p->P, ldp, Xa, ldx, cmake(0, 0), p->Y, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
+    launch_zgemm(1, 0, 2 * kb, ncols, m, cmake(1, 0), p->P + m, ldp, Xb, ldx, cmake(1, 0), p->Y, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
+    // TY = T Y
+    launch_zgemm(0, 0, 2 * kb, ncols, 2 * kb, cmake(1, 0), p->T, 2 * (size_t)kb, p->Y, 2 * (size_t)kb, cmake(0, 0), p->TY,
+                 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
+    // X -= P TY   (batch 0: a-rows, batch 1: b-rows)
+    launch_zgemm(0, 0, m, ncols, 2 * kb, cmake(-1, 0), p->P, ldp, p->TY, 2 * (size_t)kb, cmake(1, 0), Xa, ldx, 0, 2,
+                 (size_t)m, 0, (size_t)n, st);
+    p->launches += 6;
+  }
+}
+
+// full solve on device-resident operands.  Dfull: 2n x 2n complex (ld), left half = input.
+static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, cudaStream_t st) {
+  const int n = p->n;
+  PanelWs& w = p->pw;
+  w.A = Dfull;
+  w.lda = ld;
+  p->launches = 0;
+  cudaMemsetAsync(p->info_dev, 0, sizeof(int), st);
+  cudaEventRecord(p->ev[1], st);
+  tridiagonalise(p, st);
+  launch_check_finite(n, w.d, w.e, p->info_dev, st);
+  cudaEventRecord(p->ev[2], st);
+  if (!jobz) {
+    launch_bisect(n, w.d, w.e, eig_dev, p->bis, st);
+    cudaEventRecord(p->ev[3], st);
+    cudaEventRecord(p->ev[4], st);
+  } else {
+    if (!p->dc) {
+      p->dc = dc_create(n);
+      if (!p->dc) return zq_cuda_fail(cudaGetLastError(), __FILE__, __LINE__);
+    }
+    double* Z = nullptr;
+    int* perm = nullptr;
+    int rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st);
+    if (rc) return rc;
+    cudaEventRecord(p->ev[3], st);
+    cplx* X = Dfull + (size_t)n * ld;          // right half is scratch until the pairing
+    launch_phase_chain(n, w.alpha, w.e, p->s, st);
+    launch_scale_Z(n, Z, (size_t)n, perm, p->s, X, ld, st);
+    backtransform(p, X, ld, n, st);
+    launch_swap_pairing(n, Dfull, ld, st);
+    cudaEventRecord(p->ev[4], st);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return zq_cuda_fail(e, __FILE__, __LINE__);
+  return 0;
+}
+
+static void collect_phases(Plan* p, bool host_mode) {
+  float t;
+  double* ms = p->phase_ms;
+  for (int i = 0; i < 8; ++i) ms[i] = 0;
+  if (host_mode && cudaEventElapsedTime(&t, p->ev[0], p->ev[1]) == cudaSuccess) ms[0] = t;
+  if (cudaEventElapsedTime(&t, p->ev[1], p->ev[2]) == cudaSuccess) ms[1] = t;
+  if (cudaEventElapsedTime(&t, p->ev[2], p->ev[3]) == cudaSuccess) ms[2] = t;
+  if (cudaEventElapsedTime(&t, p->ev[3], p->ev[4]) == cudaSuccess) ms[3] = t;
+  if (host_mode && cudaEventElapsedTime(&t, p->ev[4], p->ev[5]) == cudaSuccess) ms[4] = t;
+  if (cudaEventElapsedTime(&t, p->ev[1], p->ev[4]) == cudaSuccess) ms[5] = t;
+  if (g_profile && p->k1ev.size() >= 2 * (size_t)p->n) {
+    double tot = 0;
+    for (int k = 0; k + 1 < p->n; ++k)
+      if (cudaEventElapsedTime(&t, p->k1ev[2 * k], p->k1ev[2 * k + 1]) == cudaSuccess) tot += t;
+    ms[6] = tot;
+  }
+  ms[7] = (double)p->launches;
+}
+
+static int check_args(int n2, void* D, int ld2, double* eig) {
+  if (n2 < 0 || (n2 & 1)) return -1;
+  if (!D) return -2;
+  if (ld2 < n2) return -3;
+  if (!eig) return -4;
+  return 0;
+}
+
+static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* opt) {
+  int rc = check_args(n2, D, ld2, eig);
+  if (rc) return rc;
+  if (n2 == 0) return 0;
+  const int n = n2 / 2;
+  const int jobz = opt ? opt->jobz : 1;
+  const int devp = opt ? opt->device_ptrs : 0;
+  int nb = (opt && opt->nb > 0) ? opt->nb : DEFAULT_NB;
+  if (nb > MAX_NB) nb = MAX_NB;
+  cudaStream_t st = opt ? (cudaStream_t)opt->stream : (cudaStream_t)0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Plan* p = nullptr;
+  rc = get_plan(n, nb, &p);
+  if (rc) return rc;
+  if (devp) {
+    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, st);
+    if (rc) return rc;
+    if (opt && opt->sync) {
+      int info = 0;
+      ZQ_CUDA_CHECK(cudaMemcpyAsync(&info, p->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+      ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+      collect_phases(p, false);
+      return info;
+    }
+    return 0;
+  }
+  // host pointers: stage through a device copy of the full 2n x 2n array
+  const size_t ld = (size_t)n2;
+  if (!p->Dfull) ZQ_CUDA_CHECK(cudaMalloc(&p->Dfull, ld * n2 * sizeof(cplx)));
+  cudaEventRecord(p->ev[0], st);
+  ZQ_CUDA_CHECK(cudaMemcpy2DAsync(p->Dfull, ld * sizeof(cplx), D, (size_t)ld2 * sizeof(cplx), (size_t)n2 * sizeof(cplx),
+                                  (size_t)n, cudaMemcpyHostToDevice, st));
+  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, st);
+  if (rc) return rc;
+  if (jobz)
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(D, (size_t)ld2 * sizeof(cplx), p->Dfull, ld * sizeof(cplx), (size_t)n2 * sizeof(cplx),
+                                    (size_t)n2, cudaMemcpyDeviceToHost, st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(eig, p->eig_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  int info = 0;
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(&info, p->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  cudaEventRecord(p->ev[5], st);
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  collect_phases(p, true);
+  return info;
+}
+
+}  // namespace zq
+
+using namespace zq;
+
+extern "C" {
+
+int zquatev_b200(int n2, void* D, int ld2, double* eig) { return solve_any(n2, D, ld2, eig, nullptr); }
+
+int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt) {
+  return solve_any(n2, D, ld2, eig, opt);
+}
+
+int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig, long long strideEig,
+                         int* info) {
+  if (batch < 0) return -1;
+  int worst = 0;
+  for (int b = 0; b < batch; ++b) {
+    const int rc = solve_any(n2, (cplx*)D + (size_t)b * strideD, ld2, eig + (size_t)b * strideEig, nullptr);
+    if (info) info[b] = rc;
+    if (rc != 0 && worst == 0) worst = rc;
+  }
+  return worst;
+}
+
+void zquatev_b200_release(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_plan) { cudaDeviceSynchronize(); plan_free(g_plan); g_plan = nullptr; }
+}
+
+int zquatev_b200_last_phases(double ms[8]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_plan) return 0;
+  for (int i = 0; i < 8; ++i) ms[i] = g_plan->phase_ms[i];
+  return 1;
+}
+
+void zquatev_b200_set_profiling(int on) { g_profile = on != 0; }
+
+const char* zquatev_b200_version(void) { return "zquatev_b200 0.1 sm_100a nb=32"; }
+
+// ---- test doors ------------------------------------------------------------------------------
+int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, void* y, int reps, double* ms) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Plan* p = nullptr;
+  int rc = get_plan(n, DEFAULT_NB, &p);
+  if (rc) return rc;
+  PanelWs& w = p->pw;
+  w.A = (cplx*)A;
+  w.lda = (size_t)lda;
+  cudaStream_t st = 0;
+  ZQ_CUDA_CHECK(cudaMemsetAsync(w.vq, 0, (size_t)n * sizeof(quat), st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(w.vq + s, (const quat*)v + s, (size_t)(n - s) * sizeof(quat), cudaMemcpyDeviceToDevice, st));
+  launch_matvec_only(w, s, (quat*)y, st);   // warm-up + result
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+  for (int i = 0; i < reps; ++i) launch_matvec_only(w, s, (quat*)y, st);
+  cudaEventRecord(b, st);
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  float t = 0;
+  cudaEventElapsedTime(&t, a, b);
+  if (ms) *ms = reps > 0 ? t / reps : 0.0;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  return 0;
+}
+
+int zq_test_zgemm(int ta, int tb, int M, int N, int K, const double* alpha, const void* A, long long lda, const void* B,
+                  long long ldb, const double* beta, void* C, long long ldc, int lower, int reps, double* ms) {
+  cudaStream_t st = 0;
+  const cplx al = cmake(alpha[0], alpha[1]), be = cmake(beta[0], beta[1]);
+  launch_zgemm(ta, tb, M, N, K, al, (const cplx*)A, (size_t)lda, (const cplx*)B, (size_t)ldb, be, (cplx*)C, (size_t)ldc,
+               lower, 1, 0, 0, 0, st);
+  if (reps > 0) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    for (int i = 0; i < reps; ++i)
+      launch_zgemm(ta, tb, M, N, K, al, (const cplx*)A, (size_t)lda, (const cplx*)B, (size_t)ldb, be, (cplx*)C,
+                   (size_t)ldc, lower, 1, 0, 0, 0, st);
+    cudaEventRecord(b, st);
+    ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    float t = 0;
+    cudaEventElapsedTime(&t, a, b);
+    if (ms) *ms = t / reps;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  ZQ_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int zq_test_stedc(int n, const double* d, const double* e, double* w, double* Z) {
+  cudaStream_t st = 0;
+  DcWs* ws = dc_create(n);
+  if (!ws) return zq_cuda_fail(cudaGetLastError(), __FILE__, __LINE__);
+  int* info_dev = nullptr;
+  cudaMalloc(&info_dev, sizeof(int));
+  cudaMemsetAsync(info_dev, 0, sizeof(int), st);
+  double* Zr = nullptr;
+  int* perm = nullptr;
+  int rc = dc_solve(ws, n, d, e, w, &Zr, &perm, info_dev, st);
+  int info = 0;
+  if (rc == 0) {
+    // gather columns in ascending order: Z[:, j] = Zr[:, perm[j]]
+    std::vector<int> hperm(n);
+    cudaMemcpyAsync(hperm.data(), perm, n * sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&info, info_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    for (int j = 0; j < n; ++j)
+      cudaMemcpyAsync(Z + (size_t)j * n, Zr + (size_t)hperm[j] * n, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+    cudaStreamSynchronize(st);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) rc = zq_cuda_fail(e2, __FILE__, __LINE__);
+  }
+  cudaFree(info_dev);
+  dc_destroy(ws);
+  return rc ? rc : info;
+}
+
+int zq_test_bisect(int n, const double* d, const double* e, double* w) {
+  cudaStream_t st = 0;
+  double* scratch = nullptr;
+  ZQ_CUDA_CHECK(cudaMalloc(&scratch, ((size_t)n + 8) * 8));
+  launch_bisect(n, d, e, w, scratch, st);
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaFree(scratch);
+  ZQ_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int zq_test_tridiag(int n, int nb, void* A, long long lda, double* d, double* e, double* tau, double* alpha) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Plan* p = nullptr;
+  if (nb <= 0) nb = DEFAULT_NB;
+  if (nb > MAX_NB) nb = MAX_NB;
+  int rc = get_plan(n, nb, &p);
+  if (rc) return rc;
+  cudaStream_t st = 0;
+  p->pw.A = (cplx*)A;
+  p->pw.lda = (size_t)lda;
+  tridiagonalise(p, st);
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(d, p->pw.d, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(e, p->pw.e, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(tau, p->pw.tau, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(alpha, p->pw.alpha, (size_t)n * sizeof(quat), cudaMemcpyDeviceToDevice, st));
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  ZQ_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+// The C++ symbol of the reference (zquatev.h:54): same mangled name, forwards to the C ABI.
+namespace ts {
+int zquatev(const int n2, std::complex<double>* const D, const int nld2, double* const eig) {
+  return zquatev_b200(n2, static_cast<void*>(D), nld2, eig);
+}
+}  // namespace ts
