@@ -51,6 +51,10 @@ typedef struct zq_options {
   void* stream;      /* cudaStream_t to run on (NULL = the legacy default stream)               */
   int sync;          /* device_ptrs only: 1 = wait for completion and return info (default when
                         the struct is zero-initialised is 0 = asynchronous, info not checked)   */
+  int col0, ncols;   /* eigenvector column block [col0, col0+ncols) to back-transform and return
+                        (ncols = 0: all n).  Multi-GPU runs shard the back-transformation by
+                        eigenvector columns: columns outside the block (and their
+                        Kramers partners n+col) are left undefined.                              */
 } zq_options;
 
 /* Same contract as zquatev_b200 plus options.  With jobz = 0 D is destroyed (holds reflectors). */

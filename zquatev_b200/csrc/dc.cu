@@ -35,6 +35,7 @@ struct DcWs {
   int *col = nullptr, *ndcol = nullptr, *dfcol = nullptr, *rc1 = nullptr, *rc2 = nullptr, *kcnt = nullptr, *perm = nullptr;
   double* scale = nullptr;
   void* base = nullptr;
+  long launches = 0;
 };
 
 namespace {
@@ -427,6 +428,8 @@ DcWs* dc_create(int n) {
   return ws;
 }
 
+long dc_launches(const DcWs* ws) { return ws ? ws->launches : 0; }
+
 void dc_destroy(DcWs* ws) {
   if (!ws) return;
   if (ws->base) cudaFree(ws->base);
@@ -460,6 +463,7 @@ int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, do
     cur ^= 1;
   }
   k_dc_final_sort<<<cdiv(n, 256), 256, 0, st>>>(n, ws->d, ws->scale, wout, ws->perm);
+  ws->launches = 4 + 9 * (long)(ws->levels.size() - 1) + 1;
   *Zres = ws->Q[cur];
   *perm = ws->perm;
   cudaError_t err = cudaGetLastError();

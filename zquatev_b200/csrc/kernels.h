@@ -60,19 +60,20 @@ void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st
 void launch_build_T(const PanelWs& w, int j0, int kb, cplx* T, cudaStream_t st);
 //   phase chain s (n quats) from alpha; X0 = diag(s) Z[:, perm]
 void launch_phase_chain(int n, const quat* alpha, const double* e, quat* s, cudaStream_t st);
-void launch_scale_Z(int n, const double* Z, size_t ldz, const int* perm, const quat* s, cplx* X, size_t ldx,
+void launch_scale_Z(int n, int ncols, const double* Z, size_t ldz, const int* perm, const quat* s, cplx* X, size_t ldx,
                     cudaStream_t st);
 // K10 pairing: right half = Theta(left half)
 void launch_pairing(int n, cplx* Out, size_t ld, cudaStream_t st);
 // in-place variant used by the driver: X sits in the RIGHT half (columns n..2n-1); on exit the left
 // half holds (U;V) = X and the right half Theta(X) = (-conj V; conj U)
-void launch_swap_pairing(int n, cplx* Out, size_t ld, cudaStream_t st);
+void launch_swap_pairing(int n, int ncols, cplx* Out, size_t ld, cudaStream_t st);
 
 // K8 tridiagonal divide & conquer (dc.cu).  d,e: n ; Z: n x n (ldz) ; on exit w ascending = d[perm[.]]
 struct DcWs;
 DcWs* dc_create(int n);
 void dc_destroy(DcWs*);
 size_t dc_bytes(int n);
+long dc_launches(const DcWs* ws);
 // returns 0 / cuda error; eigenvalues (ascending) -> wout[n]; eigenvectors: column j of the result is
 // column perm[j] of Zres (pointer returned in *Zres, ld n).  info flag on device: *info_dev != 0 -> failure.
 int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, double** Zres, int** perm,

@@ -184,7 +184,7 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
 }
 
 // full solve on device-resident operands.  Dfull: 2n x 2n complex (ld), left half = input.
-static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, cudaStream_t st) {
+static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, cudaStream_t st) {
   const int n = p->n;
   PanelWs& w = p->pw;
   w.A = Dfull;
@@ -208,12 +208,14 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     int* perm = nullptr;
     int rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st);
     if (rc) return rc;
+    p->launches += dc_launches(p->dc) + 3;
     cudaEventRecord(p->ev[3], st);
     cplx* X = Dfull + (size_t)n * ld;          // right half is scratch until the pairing
     launch_phase_chain(n, w.alpha, w.e, p->s, st);
-    launch_scale_Z(n, Z, (size_t)n, perm, p->s, X, ld, st);
-    backtransform(p, X, ld, n, st);
-    launch_swap_pairing(n, Dfull, ld, st);
+    if (ncols <= 0 || col0 < 0 || col0 + ncols > n) { col0 = 0; ncols = n; }
+    launch_scale_Z(n, ncols, Z, (size_t)n, perm + col0, p->s, X + (size_t)col0 * ld, ld, st);
+    backtransform(p, X + (size_t)col0 * ld, ld, ncols, st);
+    launch_swap_pairing(n, ncols, Dfull + (size_t)col0 * ld, ld, st);
     cudaEventRecord(p->ev[4], st);
   }
   cudaError_t e = cudaGetLastError();
@@ -263,7 +265,7 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   rc = get_plan(n, nb, &p);
   if (rc) return rc;
   if (devp) {
-    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, st);
+    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, st);
     if (rc) return rc;
     if (opt && opt->sync) {
       int info = 0;
@@ -280,7 +282,7 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   cudaEventRecord(p->ev[0], st);
   ZQ_CUDA_CHECK(cudaMemcpy2DAsync(p->Dfull, ld * sizeof(cplx), D, (size_t)ld2 * sizeof(cplx), (size_t)n2 * sizeof(cplx),
                                   (size_t)n, cudaMemcpyHostToDevice, st));
-  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, st);
+  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, st);
   if (rc) return rc;
   if (jobz)
     ZQ_CUDA_CHECK(cudaMemcpy2DAsync(D, (size_t)ld2 * sizeof(cplx), p->Dfull, ld * sizeof(cplx), (size_t)n2 * sizeof(cplx),

@@ -1,4 +1,5 @@
-// K4 / K6: FP64 complex GEMM  C = alpha * op(A) * op(B) + beta * C  (column-major).
+// K4 / K6: FP64 complex GEMM  C = alpha * op(A) * op(B) + beta * C  (column-major) on the FP64
+// tensor path (DMMA, mma.sync.m8n8k4.f64).
 //
 // Serves (a) the trailing rank-2k update of the tridiagonalisation -- the ONE stacked
 // contraction [D;E] -= L R^H that replaces the eight zgemm3m calls of the reference
@@ -7,99 +8,193 @@
 // reference's forward accumulation of Q (blocked.cc:477-544) and final zgemm3m pair
 // (zquatev.cc:87-90).
 //
-// v1 kernel: 64x64x16 shared-memory tiles, 256 threads, 4x4 complex register tile per thread
-// on the FP64 FMA pipe, register-prefetch double buffering.
+// Why DMMA: on B200 the FP64 FMA pipe and the FP64 tensor path have the same measured peak
+// (tools/fp64_peak: 36.9 vs 37.1 TFLOP/s) but one DMMA replaces 8 DFMA per lane, so the issue
+// slots, register-file ports and shared-memory bandwidth that a register-tiled DFMA kernel needs
+// (v1 of this file reached 15-20 TFLOP/s) are freed.  A complex product is four real DMMAs on
+// (re, im) fragments; conjugation is a sign flip of the imaginary fragment in registers.
+//
+// Tiling: CTA tile BM x BN (64 x 128, 8 warps; or 64 x 64, 4 warps), warp tile 32 x 32, BK = 16,
+// 3-stage cp.async pipeline straight from global to (padded, bank-conflict-free) shared memory --
+// operands are stored interleaved complex exactly as in global memory, in whichever of the two
+// orientations (contiguous along the tile dimension, or contiguous along k) the caller's op needs.
 #include "kernels.h"
 
 namespace zq {
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, LDS = BM + 1;
+constexpr int BK = 16;
 
-template <int TA, int TB>
-__global__ void __launch_bounds__(256)
-k_zgemm(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t lda, const cplx* __restrict__ B,
-        size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC) {
-  const int bx = blockIdx.x, by = blockIdx.y;
-  if (lower && bx < by) return;
+ZQ_D void cp_async16(void* smem, const void* gmem, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+ZQ_D void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+ZQ_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+ZQ_D void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Operand tile in shared memory.  KCONT = false: element (t, k) at k*LD + t, LD = BT + 2
+// (global storage contiguous along the tile dimension t);  KCONT = true: element (t, k) at
+// t*LD + k, LD = BK + 4 (global storage contiguous along k).  Both paddings make the 16-byte
+// fragment loads of a quarter warp hit 8 distinct 16-byte bank groups.
+template <int BT, bool KCONT>
+struct OpTile {
+  static constexpr int LD = KCONT ? (BK + 4) : (BT + 2);
+  static constexpr int ELEMS = KCONT ? BT * LD : BK * LD;
+  // global element (t, k): KCONT ? G[k + t*ldg] : G[t + k*ldg]
+  template <int NT>
+  static ZQ_D void load(cplx* sm, const cplx* __restrict__ G, size_t ldg, int t0, int k0, int Tmax, int Kmax, int tid) {
+#pragma unroll
+    for (int e = tid; e < BT * BK; e += NT) {
+      int t, k;
+      if (KCONT) { k = e % BK; t = e / BK; } else { t = e % BT; k = e / BT; }
+      const bool ok = (t0 + t < Tmax) && (k0 + k < Kmax);
+      const cplx* src = ok ? (KCONT ? G + (size_t)(k0 + k) + (size_t)(t0 + t) * ldg
+                                    : G + (size_t)(t0 + t) + (size_t)(k0 + k) * ldg) : G;
+      cp_async16(sm + (KCONT ? t * LD + k : k * LD + t), src, ok);
+    }
+  }
+  static ZQ_D cplx frag(const cplx* sm, int t, int k) { return sm[KCONT ? t * LD + k : k * LD + t]; }
+};
+
+// TA/TB: 0 = operand used as stored, 1 = conjugate transpose.
+//   A as stored (TA=0) is M x K (contiguous along m)  -> KCONT = false
+//   A^H       (TA=1) is stored K x M (contiguous along k) -> KCONT = true, conj
+//   B as stored (TB=0) is K x N (contiguous along k)  -> KCONT = true
+//   B^H       (TB=1) is stored N x K (contiguous along n) -> KCONT = false, conj
+template <int BM, int BN, int STAGES, int TA, int TB>
+__global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32)
+k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t lda, const cplx* __restrict__ B,
+            size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC) {
+  constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
+  using TileA = OpTile<BM, TA == 1>;
+  using TileB = OpTile<BN, TB == 0>;
+  constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+
+  const int r0 = blockIdx.x * BM, c0 = blockIdx.y * BN;
+  if (lower && r0 + BM - 1 < c0) return;
   A += (size_t)blockIdx.z * sA;
   B += (size_t)blockIdx.z * sB;
   C += (size_t)blockIdx.z * sC;
-  __shared__ cplx As[BK][LDS];
-  __shared__ cplx Bs[BK][LDS];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int r0 = bx * BM, c0 = by * BN;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp % (BM / 32)) * 32, wn = (warp / (BM / 32)) * 32;
+  const int g = lane >> 2, q = lane & 3;
 
-  cplx acc[4][4];
+  // warm L2 with the C tile this CTA will read-modify-write in the epilogue
+  const bool bzero = (beta.x == 0.0 && beta.y == 0.0);
+  if (!bzero) {
+    for (int e = tid; e < BN * (BM / 8); e += NTHREADS) {
+      const int c = c0 + e / (BM / 8), r = r0 + (e % (BM / 8)) * 8;
+      if (c < N && r < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + (size_t)r + (size_t)c * ldc));
+    }
+  }
+
+  double cre[4][4][2], cim[4][4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = cmake(0, 0);
+    for (int j = 0; j < 4; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
 
-  cplx ra[4], rb[4];
-  auto gload = [&](int k0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (TA == 0) {  // A is M x K: contiguous along rows
-        const int r = r0 + (tid & 63), kk = k0 + (tid >> 6) + 4 * j;
-        ra[j] = (r < M && kk < K) ? A[(size_t)r + (size_t)kk * lda] : cmake(0, 0);
-      } else {        // A is K x M, op = conj transpose: contiguous along k
-        const int kk = k0 + (tid & 15), r = r0 + (tid >> 4) + 16 * j;
-        ra[j] = (r < M && kk < K) ? cconj(A[(size_t)kk + (size_t)r * lda]) : cmake(0, 0);
-      }
-      if (TB == 0) {  // B is K x N: contiguous along k
-        const int kk = k0 + (tid & 15), c = c0 + (tid >> 4) + 16 * j;
-        rb[j] = (c < N && kk < K) ? B[(size_t)kk + (size_t)c * ldb] : cmake(0, 0);
-      } else {        // B is N x K, op = conj transpose: contiguous along columns of C
-        const int c = c0 + (tid & 63), kk = k0 + (tid >> 6) + 4 * j;
-        rb[j] = (c < N && kk < K) ? cconj(B[(size_t)c + (size_t)kk * ldb]) : cmake(0, 0);
-      }
+  const int nk = (K + BK - 1) / BK;
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      cplx* sa = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
+      cplx* sb = sa + TileA::ELEMS;
+      TileA::template load<NTHREADS>(sa, A, lda, r0, kt * BK, M, K, tid);
+      TileB::template load<NTHREADS>(sb, B, ldb, c0, kt * BK, N, K, tid);
     }
+    cp_async_commit();
   };
-  auto sstore = [&]() {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (TA == 0) As[(tid >> 6) + 4 * j][tid & 63] = ra[j];
-      else         As[tid & 15][(tid >> 4) + 16 * j] = ra[j];
-      if (TB == 0) Bs[tid & 15][(tid >> 4) + 16 * j] = rb[j];
-      else         Bs[(tid >> 6) + 4 * j][tid & 63] = rb[j];
-    }
-  };
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
 
-  gload(0);
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    sstore();
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
     __syncthreads();
-    if (k0 + BK < K) gload(k0 + BK);
+    issue(kt + STAGES - 1);
+    const cplx* sa = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
+    const cplx* sb = sa + TileA::ELEMS;
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      cplx a[4], b[4];
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      double ar[4], ai[4], nai[4], br[4], bi[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+      for (int i = 0; i < 4; ++i) {
+        const cplx a = TileA::frag(sa, wm + 8 * i + g, k4 + q);
+        ar[i] = a.x;
+        ai[i] = TA ? -a.y : a.y;
+        nai[i] = -ai[i];
+      }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+      for (int j = 0; j < 4; ++j) {
+        const cplx b = TileB::frag(sb, wn + 8 * j + g, k4 + q);
+        br[j] = b.x;
+        bi[j] = TB ? -b.y : b.y;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cfma(acc[i][j], a[i], b[j]);
-    }
-    __syncthreads();
-  }
-  const bool bzero = (beta.x == 0.0 && beta.y == 0.0);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 16 * j;
-    if (c >= N) continue;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + tx + 16 * i;
-      if (r >= M || (lower && r < c)) continue;
-      cplx v = cmul(alpha, acc[i][j]);
-      cplx* cp = C + (size_t)r + (size_t)c * ldc;
-      if (!bzero) { cplx o = *cp; cfma(v, beta, o); }
-      *cp = v;
+        for (int j = 0; j < 4; ++j) {
+          dmma(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
+          dmma(cim[i][j][0], cim[i][j][1], ar[i], bi[j]);
+          dmma(cre[i][j][0], cre[i][j][1], nai[i], bi[j]);
+          dmma(cim[i][j][0], cim[i][j][1], ai[i], br[j]);
+        }
     }
   }
+  cp_async_wait<0>();
+
+  // epilogue: lane holds rows wm+8i+g, columns wn+8j+2q+{0,1}
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + wn + 8 * j + 2 * q + h;
+      if (c >= N) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + wm + 8 * i + g;
+        if (r >= M || (lower && r < c)) continue;
+        cplx v = cmul(alpha, cmake(cre[i][j][h], cim[i][j][h]));
+        cplx* cp = C + (size_t)r + (size_t)c * ldc;
+        if (!bzero) { const cplx o = *cp; cfma(v, beta, o); }
+        *cp = v;
+      }
+    }
+}
+
+template <int BM, int BN, int STAGES, int TA, int TB>
+void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
+                size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st) {
+  using TileA = OpTile<BM, TA == 1>;
+  using TileB = OpTile<BN, TB == 0>;
+  constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
+  const size_t smem = (size_t)STAGES * (TileA::ELEMS + TileB::ELEMS) * sizeof(cplx);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_zgemm_mma<BM, BN, STAGES, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  dim3 g((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
+  k_zgemm_mma<BM, BN, STAGES, TA, TB><<<g, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
+}
+
+template <int TA, int TB>
+void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
+              size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st) {
+  // big tile when it still gives every SM work; the small tile fills the machine for skinny outputs
+  const long tiles_big = (long)((M + 63) / 64) * ((N + 127) / 128) * batch;
+  if (tiles_big >= 148)
+    launch_cfg<64, 128, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+  else
+    launch_cfg<64, 64, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
 }
 
 }  // namespace
@@ -108,11 +203,10 @@ void launch_zgemm(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A
                   size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
                   size_t sC, cudaStream_t st) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
-  dim3 g((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
-  if (ta == 0 && tb == 0) k_zgemm<0, 0><<<g, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
-  else if (ta == 0 && tb == 1) k_zgemm<0, 1><<<g, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
-  else if (ta == 1 && tb == 0) k_zgemm<1, 0><<<g, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
-  else k_zgemm<1, 1><<<g, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
+  if (ta == 0 && tb == 0) launch_t<0, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+  else if (ta == 0 && tb == 1) launch_t<0, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+  else if (ta == 1 && tb == 0) launch_t<1, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+  else launch_t<1, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
 }
 
 }  // namespace zq
