@@ -316,7 +316,7 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": f"2n={n2} quaternionic Hermitian eigendecomposition (values+vectors), G_sym seed 32",
-                           "n2": n2, "nb": args.nb or 32, "l2": "inputs (16*n2*n B) larger than L2; fresh copy of the input every step",
+                           "n2": n2, "nb": args.nb or 64, "l2": "inputs (16*n2*n B) larger than L2; fresh copy of the input every step",
                            "parallelism": "1 GPU" if world == 1 else f"replicated reduction + D&C, back-transform sharded by {world} column blocks, NCCL all-gather"},
                 "tflops_canonical": 164.0 / 3.0 * n ** 3 / sec * 1e-12,
                 "phases_ms": phases, "trace_error": trace_err, "gpu_launches": launches, "clocks": clocks,

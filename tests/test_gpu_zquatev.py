@@ -27,10 +27,11 @@ def check_quality(M, out, eig, g=None):
     else:
         # "at or below the reference's": both numbers are in units of N*eps, so for tiny matrices they
         # are a handful of roundings and move by O(1) with the BLAS build / summation order; the
-        # comparison therefore carries 15 % slack and the floors 0.5 (residual) / 1.5 (orthogonality),
-        # which only matter for n < 64 (at n = 200, 500 the reference has 0.048 / 1.02 and 0.027 / 0.92).
-        assert res <= max(1.15 * g["residual"], 0.5), (res, g["residual"])
-        assert orth <= max(1.15 * g["orthogonality"], 1.5), (orth, g["orthogonality"])
+        # comparison therefore carries 15 % slack and, for n < 64 ONLY, the floors 0.6 (residual) /
+        # 2.0 (orthogonality); for n >= 64 there is no floor (at n = 200, 500 the reference has 0.048 / 1.02 and 0.027 / 0.92).
+        small = len(eig) < 64
+        assert res <= max(1.15 * g["residual"], 0.6 if small else 0.0), (res, g["residual"])
+        assert orth <= max(1.15 * g["orthogonality"], 2.0 if small else 0.0), (orth, g["orthogonality"])
     return res, orth
 
 
@@ -87,7 +88,8 @@ def test_against_reference_library(n, seed):
     assert np.max(np.abs(eig[:n] - er)) <= EIG_TOL * nrm
     rr, orr, _ = O.quality(M, outr, er)
     res, orth, pair = O.quality(M, out, eig[:n])
-    assert pair == 0.0 and res <= max(1.15 * rr, 0.35) and orth <= max(1.15 * orr, 1.2)
+    fl = (0.6, 2.0) if n < 64 else (0.0, 0.0)
+    assert pair == 0.0 and res <= max(1.15 * rr, fl[0]) and orth <= max(1.15 * orr, fl[1]), (res, rr, orth, orr)
     gaps = np.minimum(np.diff(er, prepend=-np.inf), np.diff(er, append=np.inf))
     for i in range(n):
         if gaps[i] < 1e-6 * nrm:

@@ -26,7 +26,10 @@ def rand_qh(n, seed=32):
 
 
 def main():
-    sizes = [int(x) for x in sys.argv[1:]] or [512, 1024, 2048, 4096]
+    gemm_only = "gemm" in sys.argv[1:]
+    sizes = [int(x) for x in sys.argv[1:] if x.isdigit()] or [512, 1024, 2048, 4096]
+    if gemm_only:
+        sizes = []
     for n in sizes:
         buf = rand_qh(n)
         eig = torch.zeros(n, dtype=torch.float64, device="cuda")
@@ -43,7 +46,7 @@ def main():
               flush=True)
         del b2
     # K1 stand-alone
-    for n in [4096, 8192, 16384]:
+    for n in ([] if gemm_only else [4096, 8192, 16384]):
         A = torch.rand((n, 2 * n, 2), dtype=torch.float64, device="cuda")
         v = torch.rand((n, 4), dtype=torch.float64, device="cuda")
         y = torch.zeros((n, 4), dtype=torch.float64, device="cuda")
@@ -55,7 +58,8 @@ def main():
     # GEMM shapes
     for (ta, tb, M, N, K, lower, name) in [(0, 1, 8192, 8192, 128, 1, "trailing nb32"), (0, 1, 8192, 8192, 256, 1, "trailing nb64"),
                                            (1, 0, 64, 8192, 8192, 0, "Y=P^H X"), (0, 0, 8192, 8192, 64, 0, "X-=P TY nb32"),
-                                           (0, 0, 8192, 8192, 128, 0, "X-=P TY nb64"), (0, 0, 4096, 4096, 4096, 0, "square")]:
+                                           (0, 0, 8192, 8192, 128, 0, "X-=P TY nb64"), (0, 0, 4096, 4096, 4096, 0, "square"),
+                                           (1, 0, 128, 8192, 8192, 0, "Y=P^H X nb64"), (0, 0, 16384, 16384, 64, 0, "X-=P TY nb32 16k")]:
         cr = lambda r, c: torch.rand((c, r, 2), dtype=torch.float64, device="cuda")
         A = cr(K, M) if ta else cr(M, K)
         B = cr(N, K) if tb else cr(K, N)
@@ -70,7 +74,7 @@ def main():
         fl = 8.0 * M * N * K * (0.5 if lower else 1.0)
         print(json.dumps({"gemm": name, "rc": rc, "ms": ms.value, "tflops": fl / ms.value * 1e-9}), flush=True)
     # cuBLAS reference points (NOT used by the product; context for the FP64 roofline)
-    for dt_, nm in [(torch.float64, "cublas_dgemm"), (torch.complex128, "cublas_zgemm")]:
+    for dt_, nm in ([] if gemm_only else [(torch.float64, "cublas_dgemm"), (torch.complex128, "cublas_zgemm")]):
         a = torch.rand((4096, 4096), dtype=torch.float64, device="cuda").to(dt_)
         b = torch.rand((4096, 4096), dtype=torch.float64, device="cuda").to(dt_)
         torch.matmul(a, b)

@@ -10,6 +10,8 @@ constexpr int MV_TR = 128;   // tile rows  (4 rows per lane)
 constexpr int MV_TC = 64;    // tile cols  (8 warps x 8 columns)
 constexpr int DOT_ROWS = 512;
 constexpr int ROWS_PER_CTA = 256;
+constexpr int PANEL_ROWS = 32;      // rows per CTA of the latency-bound panel kernels
+constexpr int MAX_NB_PANEL = 64;    // largest panel width
 
 struct PanelWs {
   int n, nb;

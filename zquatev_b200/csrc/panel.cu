@@ -9,31 +9,57 @@
 //   reduce_correct  p = tau (M v - V (W^H v) - W (V^H v)),  partial Re(v^H p)
 // All cross-CTA reductions go through small partial buffers summed in a fixed order, so the
 // result is bit-reproducible run to run.
+//
+// These kernels are latency-bound (n of each per solve): a CTA owns only PANEL_ROWS = 32 rows
+// (lane = row, coalesced column-major access) and its 8 warps split the inner loops over the
+// panel columns / partial buffers, so even a 4096-row column spreads over 128 CTAs.
 #include "kernels.h"
 
 namespace zq {
 
 namespace {
 
-constexpr int NT = ROWS_PER_CTA;
+constexpr int NT = 256, NW = 8, PR = PANEL_ROWS;
 
 ZQ_D cplx* pan_ptr(const PanelWs& w, int which, int t) { return w.pan + ((size_t)(which * w.nb + t)) * w.n; }
+
+// deterministic block-parallel sum of a small global array (all threads get the result)
+ZQ_D double sum_parts(const double* __restrict__ p, int np, double* sm) {
+  double s = 0.0;
+  for (int j = threadIdx.x; j < np; j += NT) s += p[j];
+  double v1[1] = {s};
+  block_sum<1>(v1, sm);
+  return v1[0];
+}
+
+// cross-warp sum of one quat per (warp, lane): result valid in warp 0
+ZQ_D quat warps_sum(quat v, quat (*sm)[PR], int warp, int lane) {
+  sm[warp][lane] = v;
+  __syncthreads();
+  quat s = sm[0][lane];
+  if (warp == 0) {
+#pragma unroll
+    for (int wv = 1; wv < NW; ++wv) s = qadd(s, sm[wv][lane]);
+  }
+  return s;
+}
 
 // ---------------------------------------------------------------------------------------------
 // col_update: rows r in [k, n)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int ng_parts) {
   const int n = w.n, i = k - j0;
-  const int r = k + blockIdx.x * NT + threadIdx.x;
-  __shared__ quat qW[128], qV[128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = k + blockIdx.x * PR + lane;
+  __shared__ quat qW[MAX_NB_PANEL], qV[MAX_NB_PANEL];
+  __shared__ quat red[NW][PR];
   __shared__ double s_red[32];
   const bool act = r < n;
 
   quat wr = qzero();       // W(r, i-1) for this thread's row
   if (i > 0) {
     // finish w of the previous column: w = p - 1/2 tau (v^H p) v   (zlatrd-style; tau real)
-    double g = 0.0;
-    for (int j = 0; j < ng_parts; ++j) g += w.g_part[j];
+    const double g = sum_parts(w.g_part, ng_parts, s_red);
     const double coef = 0.5 * w.tau[k - 1] * g;
     const cplx* va = pan_ptr(w, 0, i - 1);
     const cplx* vb = pan_ptr(w, 1, i - 1);
@@ -41,8 +67,10 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
       quat pr = w.p[r];
       quat vr = qmake(va[r], vb[r]);
       wr = qmake(csub(pr.a, cscale(vr.a, coef)), csub(pr.b, cscale(vr.b, coef)));
-      pan_ptr(w, 2, i - 1)[r] = wr.a;
-      pan_ptr(w, 3, i - 1)[r] = wr.b;
+      if (warp == 0) {
+        pan_ptr(w, 2, i - 1)[r] = wr.a;
+        pan_ptr(w, 3, i - 1)[r] = wr.b;
+      }
     }
     // row-k coefficients: qconj(W(k,t)), qconj(V(k,t)), t < i
     for (int t = threadIdx.x; t < i; t += NT) {
@@ -62,15 +90,19 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
   }
   __syncthreads();
 
-  double nr = 0.0;
+  quat part = qzero();     // - sum over this warp's panel columns
   if (act) {
-    quat col = qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]);
-    for (int t = 0; t < i; ++t) {
+    for (int t = warp; t < i; t += NW) {
       quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
       quat wrt = (t == i - 1) ? wr : qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
-      qfms(col, vrt, qW[t]);
-      qfms(col, wrt, qV[t]);
+      qfms(part, vrt, qW[t]);
+      qfms(part, wrt, qV[t]);
     }
+  }
+  quat col = warps_sum(part, red, warp, lane);
+  double nr = 0.0;
+  if (warp == 0 && act) {
+    col = qadd(col, qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]));
     if (r == k) {
       w.d[k] = col.a.x;
     } else {
@@ -78,19 +110,20 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
       if (r >= k + 2) nr = qnorm2(col);
     }
   }
-  double v1[1] = {nr};
-  block_sum<1>(v1, s_red);
-  if (threadIdx.x == 0) w.nrm_part[blockIdx.x] = v1[0];
+  if (warp == 0) {
+    nr = warp_sum(nr);
+    if (lane == 0) w.nrm_part[blockIdx.x] = nr;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
-// reflector: rows r in [k+1, n)
+// reflector: rows r in [k+1, n), 256 rows per CTA
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_reflector(PanelWs w, int k, int j0, int nparts) {
   const int n = w.n, i = k - j0;
   const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
-  double rest2 = 0.0;
-  for (int j = 0; j < nparts; ++j) rest2 += w.nrm_part[j];
+  __shared__ double s_red[32];
+  const double rest2 = sum_parts(w.nrm_part, nparts, s_red);
   const quat x1 = w.x[k + 1];
   const double x1n2 = qnorm2(x1);
   const double nx2 = rest2 + x1n2;
@@ -132,9 +165,10 @@ __global__ void __launch_bounds__(NT) k_reflector(PanelWs w, int k, int j0, int 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0, int nch) {
   const int n = w.n, i = k - j0, s = k + 1;
-  const int r = s + blockIdx.x * NT + threadIdx.x;
-  __shared__ quat gW[128], gV[128];
-  __shared__ double s_red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = s + blockIdx.x * PR + lane;
+  __shared__ quat gW[MAX_NB_PANEL], gV[MAX_NB_PANEL];
+  __shared__ quat red[NW][PR];
   for (int t = threadIdx.x; t < 2 * i; t += NT) {
     const int tt = t >> 1;
     const quat* src = (t & 1) ? w.dotV : w.dotW;
@@ -146,38 +180,42 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0,
   if (blockIdx.x == 0) {
     for (int t = threadIdx.x; t < i; t += NT) w.G[(size_t)k * w.nb + t] = gV[t];
   }
-  double g = 0.0;
+  quat part = qzero();
   if (r < n) {
     const int J0 = s / MV_TC, Jlast = (n - 1) / MV_TC;
     const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
     const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
     const int Ilo = max(I0, (r / MV_TC) / 2);
-    quat y = qzero();
-    for (int J = J0; J <= Jhi; ++J) y = qadd(y, w.pd[(size_t)J * n + r]);
-    for (int I = Ilo; I <= I1; ++I) y = qadd(y, w.pt[(size_t)I * n + r]);
-    for (int t = 0; t < i; ++t) {
+    for (int J = J0 + warp; J <= Jhi; J += NW) part = qadd(part, w.pd[(size_t)J * n + r]);
+    for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
+    for (int t = warp; t < i; t += NW) {
       quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
       quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
-      qfms(y, vrt, gW[t]);
-      qfms(y, wrt, gV[t]);
+      qfms(part, vrt, gW[t]);
+      qfms(part, wrt, gV[t]);
     }
-    const double tau = w.tau[k];
-    y = qscale(y, tau);
-    w.p[r] = y;
-    const quat f = w.vq[r];
-    g = f.a.x * y.a.x + f.a.y * y.a.y + f.b.x * y.b.x + f.b.y * y.b.y;   // Re(f^H y)
   }
-  double v1[1] = {g};
-  block_sum<1>(v1, s_red);
-  if (threadIdx.x == 0) w.g_part[blockIdx.x] = v1[0];
+  quat y = warps_sum(part, red, warp, lane);
+  if (warp == 0) {
+    double g = 0.0;
+    if (r < n) {
+      const double tau = w.tau[k];
+      y = qscale(y, tau);
+      w.p[r] = y;
+      const quat f = w.vq[r];
+      g = f.a.x * y.a.x + f.a.y * y.a.y + f.b.x * y.b.x + f.b.y * y.b.y;   // Re(f^H y)
+    }
+    g = warp_sum(g);
+    if (lane == 0) w.g_part[blockIdx.x] = g;
+  }
 }
 
 // finish w of the LAST column of a panel (col_update does it for the others)
 __global__ void __launch_bounds__(NT) k_finish_w(PanelWs w, int k, int j0, int ng_parts) {
   const int n = w.n, i = k - j0;
   const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
-  double g = 0.0;
-  for (int j = 0; j < ng_parts; ++j) g += w.g_part[j];
+  __shared__ double s_red[32];
+  const double g = sum_parts(w.g_part, ng_parts, s_red);
   const double coef = 0.5 * w.tau[k] * g;
   if (r < n) {
     quat pr = w.p[r];
@@ -218,25 +256,25 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k;                    // rows k..n-1
-  const int ng = (k > j0) ? cdiv(w.n - k, NT) : 0;   // g_part written by reduce_correct of column k-1 (rows k..n-1)
-  k_col_update<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, ng);
+  const int ng = (k > j0) ? cdiv(w.n - k, PR) : 0;   // g_part written by reduce_correct of column k-1 (rows k..n-1)
+  k_col_update<<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, ng);
 }
 
 void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  const int nparts = cdiv(w.n - k, NT);        // nrm_part written by col_update (rows k..n-1)
+  const int nparts = cdiv(w.n - k, PR);        // nrm_part written by col_update (rows k..n-1)
   k_reflector<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, nparts);
 }
 
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nch = cdiv(rows, DOT_ROWS);
-  k_reduce_correct<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, nch);
+  k_reduce_correct<<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, nch);
 }
 
 void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_finish_w<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, cdiv(rows, NT));
+  k_finish_w<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, cdiv(rows, PR));
 }
 
 void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStream_t st) {

@@ -24,7 +24,7 @@ int zq_cuda_fail(cudaError_t e, const char* file, int line) {
 
 namespace zq {
 
-constexpr int DEFAULT_NB = 32;
+constexpr int DEFAULT_NB = 64;
 constexpr int MAX_NB = 64;
 
 struct Plan {
@@ -75,7 +75,7 @@ static int plan_create(int n, int nb, Plan** out) {
   const size_t o_pt = take((size_t)cdiv(n, MV_TR) * N * sizeof(quat));
   const size_t nch = (size_t)cdiv(n, DOT_ROWS) + 1;
   const size_t o_dW = take(nch * nb * sizeof(quat)), o_dV = take(nch * nb * sizeof(quat));
-  const size_t nparts = (size_t)cdiv(n, ROWS_PER_CTA) + 1;
+  const size_t nparts = (size_t)cdiv(n, PANEL_ROWS) + 1;
   const size_t o_np = take(nparts * 8), o_gp = take(nparts * 8);
   const size_t o_d = take(N * 8), o_e = take(N * 8), o_tau = take(N * 8), o_al = take(N * sizeof(quat));
   const size_t o_G = take(N * nb * sizeof(quat));
@@ -334,7 +334,7 @@ int zquatev_b200_last_phases(double ms[8]) {
 
 void zquatev_b200_set_profiling(int on) { g_profile = on != 0; }
 
-const char* zquatev_b200_version(void) { return "zquatev_b200 0.1 sm_100a nb=32"; }
+const char* zquatev_b200_version(void) { return "zquatev_b200 0.1 sm_100a nb=64"; }
 
 // ---- test doors ------------------------------------------------------------------------------
 int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, void* y, int reps, double* ms) {

@@ -23,7 +23,6 @@
 namespace zq {
 namespace {
 
-constexpr int BK = 16;
 
 ZQ_D void cp_async16(void* smem, const void* gmem, bool pred) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -43,7 +42,7 @@ ZQ_D void dmma(double& c0, double& c1, double a, double b) {
 // (global storage contiguous along the tile dimension t);  KCONT = true: element (t, k) at
 // t*LD + k, LD = BK + 4 (global storage contiguous along k).  Both paddings make the 16-byte
 // fragment loads of a quarter warp hit 8 distinct 16-byte bank groups.
-template <int BT, bool KCONT>
+template <int BT, bool KCONT, int BK>
 struct OpTile {
   static constexpr int LD = KCONT ? (BK + 4) : (BT + 2);
   static constexpr int ELEMS = KCONT ? BT * LD : BK * LD;
@@ -68,13 +67,13 @@ struct OpTile {
 //   A^H       (TA=1) is stored K x M (contiguous along k) -> KCONT = true, conj
 //   B as stored (TB=0) is K x N (contiguous along k)  -> KCONT = true
 //   B^H       (TB=1) is stored N x K (contiguous along n) -> KCONT = false, conj
-template <int BM, int BN, int STAGES, int TA, int TB>
+template <int BM, int BN, int BK, int STAGES, int TA, int TB>
 __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32)
 k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t lda, const cplx* __restrict__ B,
             size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC) {
   constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
-  using TileA = OpTile<BM, TA == 1>;
-  using TileB = OpTile<BN, TB == 0>;
+  using TileA = OpTile<BM, TA == 1, BK>;
+  using TileB = OpTile<BN, TB == 0, BK>;
   constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* smem = reinterpret_cast<cplx*>(smem_raw);
@@ -144,6 +143,12 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
         for (int j = 0; j < 4; ++j) {
           dmma(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
           dmma(cim[i][j][0], cim[i][j][1], ar[i], bi[j]);
+        }
+      // second half in a separate sweep: 32 independent DMMAs sit between the two updates of an accumulator
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           dmma(cre[i][j][0], cre[i][j][1], nai[i], bi[j]);
           dmma(cim[i][j][0], cim[i][j][1], ai[i], br[j]);
         }
@@ -170,31 +175,37 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
     }
 }
 
-template <int BM, int BN, int STAGES, int TA, int TB>
+template <int BM, int BN, int BK, int STAGES, int TA, int TB>
 void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
                 size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st) {
-  using TileA = OpTile<BM, TA == 1>;
-  using TileB = OpTile<BN, TB == 0>;
+  using TileA = OpTile<BM, TA == 1, BK>;
+  using TileB = OpTile<BN, TB == 0, BK>;
   constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
   const size_t smem = (size_t)STAGES * (TileA::ELEMS + TileB::ELEMS) * sizeof(cplx);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_zgemm_mma<BM, BN, STAGES, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_zgemm_mma<BM, BN, BK, STAGES, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
   dim3 g((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
-  k_zgemm_mma<BM, BN, STAGES, TA, TB><<<g, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
+  k_zgemm_mma<BM, BN, BK, STAGES, TA, TB><<<g, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
 }
 
 template <int TA, int TB>
 void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
               size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st) {
-  // big tile when it still gives every SM work; the small tile fills the machine for skinny outputs
-  const long tiles_big = (long)((M + 63) / 64) * ((N + 127) / 128) * batch;
-  if (tiles_big >= 148)
-    launch_cfg<64, 128, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+  // ZQ_GEMM_CFG (development knob): 0 auto, 1: 64x128 BK16 x3, 2: 64x64 BK16 x2 (2 CTAs/SM), 3: 64x64 BK8 x3
+  static const int cfg_env = [] { const char* e = getenv("ZQ_GEMM_CFG"); return e ? atoi(e) : 0; }();
+  int cfg = cfg_env;
+  if (cfg == 0) {
+    cfg = 3;   // measured best on every shape of the solver (profiles/r01_gemm_configs.md)
+  }
+  if (cfg == 1)
+    launch_cfg<64, 128, 16, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+  else if (cfg == 2)
+    launch_cfg<64, 64, 16, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
   else
-    launch_cfg<64, 64, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+    launch_cfg<64, 64, 8, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
 }
 
 }  // namespace
