@@ -25,19 +25,9 @@ constexpr int TR = MV_TR, TC = MV_TC, RI = TR / 32, NW = 8, CW = TC / NW;
 
 struct TileIdx { int I, J; };
 
-ZQ_D TileIdx decode_tile(int t, int s, int n) {
-  const int I0 = s / TR, J0 = s / TC, Jlast = (n - 1) / TC;
-  int I = I0;
-  for (;;) {
-    const int cnt = min(2 * I + 1, Jlast) - J0 + 1;
-    if (t < cnt) break;
-    t -= cnt;
-    ++I;
-  }
-  TileIdx ti; ti.I = I; ti.J = J0 + t;
-  return ti;
-}
-
+// Tiles are launched as a 2-D grid (x = row block, y = column block).  x runs fastest, so the CTAs
+// resident at any moment stream long contiguous runs of the same 64 columns instead of 2 KB
+// pieces of every column (DRAM-page friendly); grid cells above the diagonal exit at once.
 inline int count_tiles(int s, int n) {
   const int I0 = s / TR, I1 = (n - 1) / TR, J0 = s / TC, Jlast = (n - 1) / TC;
   int tot = 0;
@@ -97,13 +87,14 @@ ZQ_D void tile_body(const cplx* __restrict__ A, size_t lda, int n, int r0, int c
 
 __global__ void __launch_bounds__(256, 2)
 k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __restrict__ vq, quat* __restrict__ pd,
-         quat* __restrict__ pt, int ntiles,
+         quat* __restrict__ pt, int nI,
          // fused panel dots
          const cplx* __restrict__ pan, int nb, int ncols, quat* __restrict__ dotW, quat* __restrict__ dotV) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if ((int)blockIdx.x >= ntiles) {
-    // ---- panel inner products: chunk of DOT_ROWS rows, warp per column t ----
-    const int ch = blockIdx.x - ntiles;
+  if ((int)blockIdx.x >= nI) {
+    // ---- panel inner products: chunk of DOT_ROWS rows, warp per column t (only in grid row y = 0) ----
+    if (blockIdx.y != 0) return;
+    const int ch = blockIdx.x - nI;
     const int ra = s + ch * DOT_ROWS, rb = min(n, ra + DOT_ROWS);
     for (int t = warp; t < ncols; t += NW) {
       const cplx* va = pan + ((size_t)(0 * nb + t)) * n;
@@ -127,7 +118,10 @@ k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __res
   }
   __shared__ quat vcol[TC];
   __shared__ quat red[NW][TR];
-  const TileIdx ti = decode_tile(blockIdx.x, s, n);
+  TileIdx ti;
+  ti.I = s / TR + blockIdx.x;
+  ti.J = s / TC + blockIdx.y;
+  if (2 * ti.I + 1 < ti.J) return;                      // tile entirely above the diagonal
   const int r0 = ti.I * TR, c0 = ti.J * TC;
   if (threadIdx.x < TC) {
     const int c = c0 + threadIdx.x;
@@ -173,16 +167,16 @@ __global__ void k_matvec_gather(int n, int s, const quat* pd, const quat* pt, qu
 
 void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int s = k + 1, n = w.n;
-  const int ntiles = count_tiles(s, n);
+  const int nI = (n - 1) / TR - s / TR + 1, nJ = (n - 1) / TC - s / TC + 1;
   const int ncols = k - j0;
   const int nch = ncols > 0 ? (n - s + DOT_ROWS - 1) / DOT_ROWS : 0;
-  k_matvec<<<ntiles + nch, 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, ntiles, w.pan, w.nb, ncols, w.dotW, w.dotV);
+  k_matvec<<<dim3(nI + nch, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, w.pan, w.nb, ncols, w.dotW, w.dotV);
 }
 
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st) {
   const int n = w.n;
-  const int ntiles = count_tiles(s, n);
-  k_matvec<<<ntiles, 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, ntiles, w.pan, w.nb, 0, w.dotW, w.dotV);
+  const int nI = (n - 1) / TR - s / TR + 1, nJ = (n - 1) / TC - s / TC + 1;
+  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, w.pan, w.nb, 0, w.dotW, w.dotV);
   k_matvec_gather<<<(n - s + 255) / 256, 256, 0, st>>>(n, s, w.pd, w.pt, y);
 }
 
