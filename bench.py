@@ -9,9 +9,11 @@ step    : one complete solve of one synthetic matrix (G_sym: uniform [-1/2,1/2) 
 value   : device-resident (input already in HBM, result left in HBM), max over ranks.
 e2e     : the same solve through the reference-facing C ABI `zquatev_b200_ex` with HOST (pinned)
           buffers: H2D of the left half and D2H of all 2n columns inside the timed region.
-N > 1   : strong scaling (the problem is fixed).  Round 1 shards the back-transformation by
-          eigenvector columns and all-gathers the blocks over NCCL; the reduction
-          and the tridiagonal solve are replicated on every rank.
+N > 1   : strong scaling (the problem is fixed).  One collective solve: D and E distributed 1-D
+          block-cyclic by 64-column blocks (per column one NCCL broadcast of the reflector and one
+          all-reduce of the partial mat-vec), trailing update on owned blocks only, back-transformation
+          sharded by eigenvector columns, result gathered on every rank; the tridiagonal D&C is
+          replicated.
 --impl reference : the UNMODIFIED reference ts::zquatev built in oracle/_ref, timed on the host
           cores on a bounded sample (2n = 2048) and scaled by n^3 to the workload (SURVEY.md 8d:
           a real 2n=32768 CPU run takes ~12 h).
@@ -183,13 +185,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
+        from zquatev_b200 import dist as zd
+        zd.init_from_torch()                                      # the solver's own NCCL communicator
     n2 = args.n2
     n = n2 // 2
-    if n % world:
-        raise SystemExit("n must be divisible by the number of GPUs")
-    ncols = n // world
-    col0 = rank * ncols
 
     def barrier():
         if world > 1:
@@ -203,13 +204,10 @@ def main():
 
     def step_device():
         work[:n].copy_(left0)                                     # restore the (destroyed) input: D2D, 16 n^2 B
+        # N > 1: ONE collective call; reduction 1-D block-cyclic over the ranks, back-transformation
+        # split by eigenvector columns, result complete on every rank (NCCL inside the library)
         info = z.zquatev_device(n2, work.data_ptr(), n2, eig.data_ptr(), nb=args.nb, stream=stream, sync=True,
-                                col0=col0, ncols=ncols if world > 1 else 0)
-        if world > 1:
-            blkL = work[col0:col0 + ncols].clone()
-            blkR = work[n + col0:n + col0 + ncols].clone()
-            dist.all_gather_into_tensor(work[:n].view(-1), blkL.view(-1))
-            dist.all_gather_into_tensor(work[n:].view(-1), blkR.view(-1))
+                                dist=world > 1)
         return info
 
     for _ in range(args.warmup):
@@ -224,7 +222,7 @@ def main():
     launches = 0
     for _ in range(args.steps):
         info = step_device()
-        launches += int(z.last_phases()["launches"]) + 1 + (2 if world > 1 else 0)
+        launches += int(z.last_phases()["launches"]) + 1
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -241,14 +239,16 @@ def main():
 
     # ---- roofline of the dominant kernel (K1): one extra profiled step, per-launch CUDA events ----
     roof = None
+    z.set_profiling(True)                                         # collective for N > 1: every rank runs it
+    step_device()
+    torch.cuda.synchronize()
+    ph = z.last_phases()
+    z.set_profiling(False)
+    barrier()
     if rank == 0:
-        z.set_profiling(True)
-        step_device()
-        torch.cuda.synchronize()
-        ph = z.last_phases()
-        z.set_profiling(False)
         k1_ms = ph["k1_matvec"]
-        alg_bytes = sum(16.0 * (n - k - 1) ** 2 + 64.0 * (n - k - 1) for k in range(n - 1))   # lower triangles of D,E + v,y
+        # lower triangles of D,E + v,y; with N ranks each rank streams 1/N of the column blocks
+        alg_bytes = sum(16.0 * (n - k - 1) ** 2 / world + 64.0 * (n - k - 1) for k in range(n - 1))
         peaks, src = measured_peaks()
         ach = alg_bytes / (k1_ms * 1e-3) * 1e-9 if k1_ms > 0 else None
         roof = {"kernel": "k_matvec (K1 quaternion-Hermitian mat-vec, lower triangles)", "bound": "hbm",
@@ -262,6 +262,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
+            import psutil
+            need = world * (16.0 * n2 * n2 + 16.0 * n2 * n) * 1.15            # every rank pins the full array
+            if psutil.virtual_memory().available < need:
+                raise MemoryError(f"host RAM: need {need / 2**30:.0f} GiB for {world} pinned arrays")
             host = torch.empty((n2, n2), dtype=torch.complex128, pin_memory=True)
             host0 = left0.cpu()
             eig_h = np.zeros(n2)
@@ -273,7 +277,7 @@ def main():
                 host[:n].copy_(host0)
                 barrier()
                 t0 = time.perf_counter()
-                opt = z.ZqOptions(1, 0, args.nb, None, 1, 0, 0)
+                opt = z.ZqOptions(1, 0, args.nb, None, 1, 0, 0, 1 if world > 1 else 0)
                 info = z.lib().zquatev_b200_ex(n2, ctypes.c_void_p(host.data_ptr()), n2, eig_h.ctypes.data, ctypes.byref(opt))
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
@@ -285,8 +289,7 @@ def main():
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e = {"value": te.item(), "unit": "s", "h2d_bytes_per_step": 16 * n2 * n, "d2h_bytes_per_step": 16 * n2 * n2 + 8 * n,
                    "phases_ms": z.last_phases(),
-                   "note": "host-pointer C ABI call zquatev_b200_ex (== ts::zquatev), pinned host array; single-GPU path per rank" if world > 1 else
-                           "host-pointer C ABI call zquatev_b200_ex (== ts::zquatev), pinned host array"}
+                   "note": "host-pointer C ABI call zquatev_b200_ex (== ts::zquatev), pinned host array" + ("; every rank uploads its copy and downloads the full result" if world > 1 else "")}
         except Exception as ex:   # e.g. not enough pinned host memory on the box
             e2e = {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
 
@@ -317,12 +320,14 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"2n={n2} quaternionic Hermitian eigendecomposition (values+vectors), G_sym seed 32",
                            "n2": n2, "nb": args.nb or 64, "l2": "inputs (16*n2*n B) larger than L2; fresh copy of the input every step",
-                           "parallelism": "1 GPU" if world == 1 else f"replicated reduction + D&C, back-transform sharded by {world} column blocks, NCCL all-gather"},
+                           "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: reduction 1-D block-cyclic (64-column blocks) with per-column NCCL broadcast + all-reduce, D&C replicated, back-transform sharded by eigenvector columns, NCCL gather of the result"},
                 "tflops_canonical": 164.0 / 3.0 * n ** 3 / sec * 1e-12,
                 "phases_ms": phases, "trace_error": trace_err, "gpu_launches": launches, "clocks": clocks,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
         print(json.dumps(line), flush=True)
     if world > 1:
+        from zquatev_b200 import dist as zd
+        zd.finalize()
         dist.destroy_process_group()
 
 

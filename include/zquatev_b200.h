@@ -55,6 +55,11 @@ typedef struct zq_options {
                         (ncols = 0: all n).  Multi-GPU runs shard the back-transformation by
                         eigenvector columns: columns outside the block (and their
                         Kramers partners n+col) are left undefined.                              */
+  int dist;          /* 1: collective multi-GPU solve over the communicator made by
+                        zquatev_b200_dist_init: every rank calls with the SAME input (its own copy);
+                        D and E are treated as distributed 1-D block-cyclic by 64-column blocks, the
+                        back-transformation is split by eigenvector columns, and on return every
+                        rank holds the complete result.  Needs nb = 64.                           */
 } zq_options;
 
 /* Same contract as zquatev_b200 plus options.  With jobz = 0 D is destroyed (holds reflectors). */
@@ -65,6 +70,13 @@ int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt
  * Host pointers.  The reference has no batched entry -- its callers loop over zquatev().      */
 int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig,
                          long long strideEig, int* info);
+
+/* Multi-GPU (one process per GPU, NCCL over NVLink).  Rank 0 creates a 128-byte NCCL
+ * unique id, the caller ships it to the other ranks (e.g. torch.distributed.broadcast), then every
+ * rank calls dist_init on its own CUDA device.  libnccl.so.2 is loaded lazily by these calls.   */
+int zquatev_b200_dist_unique_id(void* id128);
+int zquatev_b200_dist_init(int rank, int world, const void* id128);
+void zquatev_b200_dist_finalize(void);
 
 /* Workspace cache: plans (device workspaces for one n) are created on first use and cached per
  * thread-safe global table; this frees them.                                                  */

@@ -1,0 +1,74 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic: the NCCL unique id travels through
+torch.distributed, and the column partitions used by the solver cover the problem exactly."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from zquatev_b200 import dist as zd
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        raw = zd.exchange_unique_id(zd._make_nccl_id)
+        # the ranks also agree on who owns what
+        n = 1000
+        blocks = [zd.column_block(r, world, n) for r in range(world)]
+        t = torch.tensor([sum(raw) % 65521, blocks[rank][0], blocks[rank][1]], dtype=torch.int64)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        q.put((rank, raw, [g.tolist() for g in gathered]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unique_id_exchange_gloo_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    assert res[0][1] == res[1][1] and len(res[0][1]) == 128 and any(res[0][1])
+    g = res[0][2]
+    assert g[0][0] == g[1][0]                       # same id checksum seen by both ranks
+    assert g[0][1] == 0 and g[0][1] + g[0][2] == g[1][1] and g[1][1] + g[1][2] == 1000
+
+
+@pytest.mark.parametrize("n,world", [(1, 2), (7, 8), (64, 8), (1000, 3), (16384, 8), (100, 1)])
+def test_column_blocks_partition(n, world):
+    cover = []
+    for r in range(world):
+        c0, nc = zd.column_block(r, world, n)
+        assert 0 <= c0 <= n and nc >= 0
+        cover += list(range(c0, c0 + nc))
+    assert cover == list(range(n))
+
+
+def test_block_cyclic_owner():
+    world = 4
+    owners = [zd.owner_of_column(k, world) for k in range(64 * 9)]
+    assert owners[0] == 0 and owners[63] == 0 and owners[64] == 1 and owners[64 * 4] == 0 and owners[64 * 7 + 5] == 3
+    # every rank owns the same number of blocks (+-1)
+    cnt = [sum(1 for b in range(9) if b % world == r) for r in range(world)]
+    assert max(cnt) - min(cnt) <= 1

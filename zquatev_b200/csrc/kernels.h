@@ -32,12 +32,22 @@ struct PanelWs {
   double* tau;        // [n]
   quat* alpha;        // [n]   quaternion sub-diagonal
   quat* G;            // [n][nb] saved V^H v_i (strict upper part of the panel Gram matrix)
+  // multi-GPU (1-D block-cyclic by 64-column blocks): this rank owns column blocks
+  // J with J % world == rank.  world == 1: single GPU.
+  int rank, world;
 };
 
 // K2/K3 panel column kernels (panel.cu)
 void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st);
 void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st);
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
+// distributed variants: (1) y_local = sum of this rank's K1 partials -> w.p rows [k+1, n);
+// (2) after the all-reduce of w.p: corrections, tau scaling, partial Re(v^H p)
+void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st);
+void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
+// after the broadcast of vq[k+1 .. n+2) from the owner of column k: store v into the panel, the
+// reflector storage of A and the scalars d,e,tau,alpha (vq[n] = (d,e,tau,0), vq[n+1] = alpha)
+void launch_unpack_v(const PanelWs& w, int k, int j0, cudaStream_t st);
 void launch_finish_w(const PanelWs& w, int k_last, int j0, cudaStream_t st);
 // K1 quaternion-Hermitian mat-vec on the lower triangles (+ fused panel dot products)
 void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st);
@@ -54,6 +64,10 @@ void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStr
 void launch_zgemm(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
                   size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
                   size_t sC, cudaStream_t st);
+// same, restricted to the 64-column blocks cb0, cb0+cbs, cb0+2*cbs, ... (ncb of them) of C
+void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
+                     size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
+                     size_t sC, int cb0, int cbs, int ncb, cudaStream_t st);
 
 // K6 helpers (backtransform.cu)
 //   P = Phi(V) of panel [j0, j0+kb): (2m x 2kb), ld 2m, m = n-1-j0 ; rows [0,m) <-> a-part rows j0+1..

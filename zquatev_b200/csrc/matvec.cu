@@ -87,7 +87,7 @@ ZQ_D void tile_body(const cplx* __restrict__ A, size_t lda, int n, int r0, int c
 
 __global__ void __launch_bounds__(256, 2)
 k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __restrict__ vq, quat* __restrict__ pd,
-         quat* __restrict__ pt, int nI,
+         quat* __restrict__ pt, int nI, int jfirst, int jstride,
          // fused panel dots
          const cplx* __restrict__ pan, int nb, int ncols, quat* __restrict__ dotW, quat* __restrict__ dotV) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -120,8 +120,8 @@ k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __res
   __shared__ quat red[NW][TR];
   TileIdx ti;
   ti.I = s / TR + blockIdx.x;
-  ti.J = s / TC + blockIdx.y;
-  if (2 * ti.I + 1 < ti.J) return;                      // tile entirely above the diagonal
+  ti.J = jfirst + blockIdx.y * jstride;                 // owned column blocks only (multi-GPU)
+  if (2 * ti.I + 1 < ti.J || ti.J * TC >= n) return;    // tile entirely above the diagonal / no owned block
   const int r0 = ti.I * TR, c0 = ti.J * TC;
   if (threadIdx.x < TC) {
     const int c = c0 + threadIdx.x;
@@ -165,18 +165,28 @@ __global__ void k_matvec_gather(int n, int s, const quat* pd, const quat* pt, qu
 
 }  // namespace
 
+static void owned_blocks(const PanelWs& w, int s, int& jfirst, int& nJ) {
+  const int J0 = s / TC, Jlast = (w.n - 1) / TC;
+  jfirst = J0 + ((w.rank - J0 % w.world) + w.world) % w.world;
+  nJ = jfirst > Jlast ? 0 : (Jlast - jfirst) / w.world + 1;
+}
+
 void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int s = k + 1, n = w.n;
-  const int nI = (n - 1) / TR - s / TR + 1, nJ = (n - 1) / TC - s / TC + 1;
+  const int nI = (n - 1) / TR - s / TR + 1;
+  int jfirst, nJ;
+  owned_blocks(w, s, jfirst, nJ);
   const int ncols = k - j0;
   const int nch = ncols > 0 ? (n - s + DOT_ROWS - 1) / DOT_ROWS : 0;
-  k_matvec<<<dim3(nI + nch, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, w.pan, w.nb, ncols, w.dotW, w.dotV);
+  if (nJ == 0 && nch == 0) return;
+  k_matvec<<<dim3(nI + nch, nJ > 0 ? nJ : 1), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, jfirst, w.world, w.pan,
+                                                           w.nb, ncols, w.dotW, w.dotV);
 }
 
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st) {
   const int n = w.n;
   const int nI = (n - 1) / TR - s / TR + 1, nJ = (n - 1) / TC - s / TC + 1;
-  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, w.pan, w.nb, 0, w.dotW, w.dotV);
+  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, s / TC, 1, w.pan, w.nb, 0, w.dotW, w.dotV);
   k_matvec_gather<<<(n - s + 255) / 256, 256, 0, st>>>(n, s, w.pd, w.pt, y);
 }
 

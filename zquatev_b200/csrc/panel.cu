@@ -157,45 +157,89 @@ __global__ void __launch_bounds__(NT) k_reflector(PanelWs w, int k, int j0, int 
     w.alpha[k] = alpha;
     w.e[k] = nx;
     w.tau[k] = tau;
+    // scalars of this column ride behind the reflector in the broadcast buffer (multi-GPU)
+    w.vq[n] = qmake(cmake(w.d[k], nx), cmake(tau, 0.0));
+    w.vq[n + 1] = alpha;
+  }
+}
+
+// multi-GPU: vq[k+1 .. n+2) has just been broadcast from the owner of column k
+__global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, int k, int j0) {
+  const int n = w.n, i = k - j0;
+  const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
+  if (r < n) {
+    const quat v = w.vq[r];
+    pan_ptr(w, 0, i)[r] = v.a;
+    pan_ptr(w, 1, i)[r] = v.b;
+    if (r >= k + 2) {
+      w.A[(size_t)r + (size_t)k * w.lda] = v.a;
+      w.A[(size_t)(n + r) + (size_t)k * w.lda] = v.b;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const quat sc = w.vq[n];
+    w.d[k] = sc.a.x;
+    w.e[k] = sc.a.y;
+    w.tau[k] = sc.b.x;
+    w.alpha[k] = w.vq[n + 1];
+    w.vq[k] = qzero();
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // reduce_correct: rows r in [k+1, n)
 // ---------------------------------------------------------------------------------------------
+// MODE 0: single GPU (sum all K1 partials, correct, scale).  MODE 1: multi-GPU, local part only:
+// w.p[r] = sum of THIS rank's partials.  MODE 2: multi-GPU, after the all-reduce of w.p: correct, scale.
+template <int MODE>
 __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0, int nch) {
   const int n = w.n, i = k - j0, s = k + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = s + blockIdx.x * PR + lane;
   __shared__ quat gW[MAX_NB_PANEL], gV[MAX_NB_PANEL];
   __shared__ quat red[NW][PR];
-  for (int t = threadIdx.x; t < 2 * i; t += NT) {
-    const int tt = t >> 1;
-    const quat* src = (t & 1) ? w.dotV : w.dotW;
-    quat acc = qzero();
-    for (int c = 0; c < nch; ++c) acc = qadd(acc, src[(size_t)c * w.nb + tt]);
-    if (t & 1) gV[tt] = acc; else gW[tt] = acc;
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    for (int t = threadIdx.x; t < i; t += NT) w.G[(size_t)k * w.nb + t] = gV[t];
+  if (MODE != 1) {
+    for (int t = threadIdx.x; t < 2 * i; t += NT) {
+      const int tt = t >> 1;
+      const quat* src = (t & 1) ? w.dotV : w.dotW;
+      quat acc = qzero();
+      for (int c = 0; c < nch; ++c) acc = qadd(acc, src[(size_t)c * w.nb + tt]);
+      if (t & 1) gV[tt] = acc; else gW[tt] = acc;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+      for (int t = threadIdx.x; t < i; t += NT) w.G[(size_t)k * w.nb + t] = gV[t];
+    }
   }
   quat part = qzero();
   if (r < n) {
-    const int J0 = s / MV_TC, Jlast = (n - 1) / MV_TC;
-    const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
-    const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
-    const int Ilo = max(I0, (r / MV_TC) / 2);
-    for (int J = J0 + warp; J <= Jhi; J += NW) part = qadd(part, w.pd[(size_t)J * n + r]);
-    for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
-    for (int t = warp; t < i; t += NW) {
-      quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
-      quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
-      qfms(part, vrt, gW[t]);
-      qfms(part, wrt, gV[t]);
+    if (MODE != 2) {
+      const int J0 = s / MV_TC, Jlast = (n - 1) / MV_TC;
+      const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
+      const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
+      const int Ilo = max(I0, (r / MV_TC) / 2);
+      // owned column blocks only: J = jfirst, jfirst + world, ...  (world == 1: all)
+      const int jfirst = J0 + ((w.rank - J0 % w.world) + w.world) % w.world;
+      for (int J = jfirst + warp * w.world; J <= Jhi; J += NW * w.world) part = qadd(part, w.pd[(size_t)J * n + r]);
+      if ((r / MV_TC) % w.world == w.rank)     // transposed sums exist only on the owner of r's column block
+        for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
+    } else if (warp == 0) {
+      part = w.p[r];                           // all-reduced M v
+    }
+    if (MODE != 1) {
+      for (int t = warp; t < i; t += NW) {
+        quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
+        quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
+        qfms(part, vrt, gW[t]);
+        qfms(part, wrt, gV[t]);
+      }
     }
   }
   quat y = warps_sum(part, red, warp, lane);
+  if (MODE == 1) {
+    if (warp == 0 && r < n) w.p[r] = y;
+    return;
+  }
   if (warp == 0) {
     double g = 0.0;
     if (r < n) {
@@ -269,7 +313,23 @@ void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st) {
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nch = cdiv(rows, DOT_ROWS);
-  k_reduce_correct<<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, nch);
+  k_reduce_correct<0><<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, nch);
+}
+
+void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  k_reduce_correct<1><<<cdiv(rows, PR), NT, 0, st>>>(w, k, k, 0);
+}
+
+void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  const int nch = cdiv(rows, DOT_ROWS);
+  k_reduce_correct<2><<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, nch);
+}
+
+void launch_unpack_v(const PanelWs& w, int k, int j0, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  k_unpack_v<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0);
 }
 
 void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {

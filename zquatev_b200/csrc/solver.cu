@@ -14,6 +14,8 @@
 #include <cstring>
 #include <mutex>
 #include <vector>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "kernels.h"
 #include "../../include/zquatev_b200.h"
 
@@ -44,6 +46,42 @@ struct Plan {
   long launches = 0;
 };
 
+// ---- NCCL, resolved at run time (no link dependency: single-GPU users never load it) ----------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static ncclComm_t g_comm = nullptr;
+static int g_rank = 0, g_world = 1;
+
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { fprintf(stderr, "[zquatev_b200] cannot load libnccl: %s\n", dlerror()); return -900; }
+#define ZQ_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { fprintf(stderr, "[zquatev_b200] missing %s\n", name); return -901; }
+  ZQ_SYM(GetUniqueId, "ncclGetUniqueId") ZQ_SYM(CommInitRank, "ncclCommInitRank") ZQ_SYM(CommDestroy, "ncclCommDestroy")
+  ZQ_SYM(Broadcast, "ncclBroadcast") ZQ_SYM(AllReduce, "ncclAllReduce") ZQ_SYM(GroupStart, "ncclGroupStart")
+  ZQ_SYM(GroupEnd, "ncclGroupEnd") ZQ_SYM(GetErrorString, "ncclGetErrorString")
+#undef ZQ_SYM
+  g_nccl.h = h;
+  return 0;
+}
+
+static int nccl_fail(ncclResult_t r, int line) {
+  fprintf(stderr, "[zquatev_b200] NCCL error %d (%s) at solver.cu:%d\n", (int)r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?", line);
+  return -(900 + (int)r);
+}
+#define ZQ_NCCL_CHECK(expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) return nccl_fail(_r, __LINE__); } while (0)
+
 static std::mutex g_mu;
 static Plan* g_plan = nullptr;
 static bool g_profile = false;
@@ -70,7 +108,7 @@ static int plan_create(int n, int nb, Plan** out) {
   size_t bytes = 0;
   auto take = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
   const size_t o_pan = take(4 * (size_t)nb * N * sizeof(cplx));
-  const size_t o_x = take(N * sizeof(quat)), o_vq = take(N * sizeof(quat)), o_p = take(N * sizeof(quat));
+  const size_t o_x = take(N * sizeof(quat)), o_vq = take((N + 2) * sizeof(quat)), o_p = take(N * sizeof(quat));
   const size_t o_pd = take((size_t)cdiv(n, MV_TC) * N * sizeof(quat));
   const size_t o_pt = take((size_t)cdiv(n, MV_TR) * N * sizeof(quat));
   const size_t nch = (size_t)cdiv(n, DOT_ROWS) + 1;
@@ -87,7 +125,7 @@ static int plan_create(int n, int nb, Plan** out) {
   if (e != cudaSuccess) { delete p; return zq_cuda_fail(e, __FILE__, __LINE__); }
   char* b = p->slab;
   PanelWs& w = p->pw;
-  w.n = n; w.nb = nb; w.lda = 0; w.A = nullptr;
+  w.n = n; w.nb = nb; w.lda = 0; w.A = nullptr; w.rank = 0; w.world = 1;
   w.pan = (cplx*)(b + o_pan); w.x = (quat*)(b + o_x); w.vq = (quat*)(b + o_vq); w.p = (quat*)(b + o_p);
   w.pd = (quat*)(b + o_pd); w.pt = (quat*)(b + o_pt); w.dotW = (quat*)(b + o_dW); w.dotV = (quat*)(b + o_dV);
   w.nrm_part = (double*)(b + o_np); w.g_part = (double*)(b + o_gp);
@@ -155,12 +193,73 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-GPU reduction: D and E are distributed 1-D block-cyclic by 64-column blocks
+// (every rank keeps the full array but only its own blocks are kept up to date).  Per column: the
+// owner forms the reflector and broadcasts it (one NCCL broadcast of 32 m + 64 bytes), every rank
+// multiplies its own column blocks (K1), the partial products are all-reduced (32 m bytes), and the
+// panel algebra is replicated.  The trailing update touches only the owned blocks: no exchange.
+// ---------------------------------------------------------------------------------------------
+static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
+  PanelWs& w = p->pw;
+  const int n = w.n, nb = w.nb, G = g_world;
+  if (nb != MV_TC) return -5;                      // ownership granularity = K1 / GEMM column tile
+  const bool prof = g_profile;
+  if (prof && p->k1ev.size() < 2 * (size_t)n) {
+    const size_t old = p->k1ev.size();
+    p->k1ev.resize(2 * (size_t)n);
+    for (size_t i = old; i < p->k1ev.size(); ++i) cudaEventCreate(&p->k1ev[i]);
+  }
+  w.rank = g_rank;
+  w.world = G;
+  cudaMemsetAsync(w.vq, 0, (size_t)(n + 2) * sizeof(quat), st);
+  cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
+  cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
+  cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
+  for (int j0 = 0; j0 < n - 1; j0 += nb) {
+    const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
+    const int owner = (j0 / nb) % G;
+    for (int i = 0; i < kb; ++i) {
+      const int k = j0 + i, m = n - k - 1;
+      launch_col_update(w, k, j0, st);
+      if (owner == g_rank) launch_reflector(w, k, j0, st);
+      ZQ_NCCL_CHECK(g_nccl.Broadcast(w.vq + k + 1, w.vq + k + 1, (size_t)4 * (m + 2), ncclDouble, owner, g_comm, st));
+      launch_unpack_v(w, k, j0, st);
+      if (prof) cudaEventRecord(p->k1ev[2 * k], st);
+      launch_matvec(w, k, j0, st);
+      if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
+      launch_reduce_partial(w, k, st);
+      ZQ_NCCL_CHECK(g_nccl.AllReduce(w.p + k + 1, w.p + k + 1, (size_t)4 * m, ncclDouble, ncclSum, g_comm, st));
+      launch_correct(w, k, j0, st);
+      p->launches += 7;
+    }
+    launch_finish_w(w, j0 + kb - 1, j0, st);
+    const int r0 = j0 + kb, m = n - r0;
+    if (m > 0) {
+      launch_build_LR(w, r0, kb, p->L, p->R, st);
+      // owned 64-column blocks of the trailing matrix: global block (r0/64 + jt), jt = cb0, cb0 + G, ...
+      const int b0 = r0 / MV_TC, nblk = (m + MV_TC - 1) / MV_TC;
+      const int cb0 = ((g_rank - b0 % G) + G) % G;
+      const int ncb = cb0 >= nblk ? 0 : (nblk - 1 - cb0) / G + 1;
+      launch_zgemm_cb(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
+                      w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, cb0, G, ncb, st);
+      p->launches += 3;
+    }
+  }
+  launch_col_update(w, n - 1, n - 1, st);          // d[n-1]: valid on the owner of the last column block
+  ZQ_NCCL_CHECK(g_nccl.Broadcast(w.d + n - 1, w.d + n - 1, 1, ncclDouble, ((n - 1) / nb) % G, g_comm, st));
+  p->launches += 1;
+  w.rank = 0;
+  w.world = 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6: X <- H_0 ... H_{n-2} X, X = stacked (Xa; Xb), 2n x n, leading dimension ldx
 // ---------------------------------------------------------------------------------------------
 static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t st) {
   const PanelWs& w = p->pw;
   const int n = w.n, nb = w.nb;
-  if (n < 2) return;
+  if (n < 2 || ncols <= 0) return;
   const int last = ((n - 2) / nb) * nb;
   for (int j0 = last; j0 >= 0; j0 -= nb) {
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
@@ -184,7 +283,7 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
 }
 
 // full solve on device-resident operands.  Dfull: 2n x 2n complex (ld), left half = input.
-static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, cudaStream_t st) {
+static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, int dist, cudaStream_t st) {
   const int n = p->n;
   PanelWs& w = p->pw;
   w.A = Dfull;
@@ -192,7 +291,13 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   p->launches = 0;
   cudaMemsetAsync(p->info_dev, 0, sizeof(int), st);
   cudaEventRecord(p->ev[1], st);
-  tridiagonalise(p, st);
+  if (dist) {
+    if (!g_comm) return -6;
+    const int rc = tridiagonalise_dist(p, st);
+    if (rc) return rc;
+  } else {
+    tridiagonalise(p, st);
+  }
   launch_check_finite(n, w.d, w.e, p->info_dev, st);
   cudaEventRecord(p->ev[2], st);
   if (!jobz) {
@@ -212,10 +317,27 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     cudaEventRecord(p->ev[3], st);
     cplx* X = Dfull + (size_t)n * ld;          // right half is scratch until the pairing
     launch_phase_chain(n, w.alpha, w.e, p->s, st);
-    if (ncols <= 0 || col0 < 0 || col0 + ncols > n) { col0 = 0; ncols = n; }
+    if (dist) {                                 // eigenvector columns split evenly over the ranks
+      const int per = (n + g_world - 1) / g_world;
+      col0 = g_rank * per < n ? g_rank * per : n;
+      ncols = (col0 + per <= n) ? per : n - col0;
+    } else if (ncols <= 0 || col0 < 0 || col0 + ncols > n) { col0 = 0; ncols = n; }
     launch_scale_Z(n, ncols, Z, (size_t)n, perm + col0, p->s, X + (size_t)col0 * ld, ld, st);
     backtransform(p, X + (size_t)col0 * ld, ld, ncols, st);
     launch_swap_pairing(n, ncols, Dfull + (size_t)col0 * ld, ld, st);
+    if (dist) {                                 // every rank ends with all 2n columns
+      const int per = (n + g_world - 1) / g_world;
+      ZQ_NCCL_CHECK(g_nccl.GroupStart());
+      for (int r = 0; r < g_world; ++r) {
+        const int c0 = r * per < n ? r * per : n, nc = (c0 + per <= n) ? per : n - c0;
+        if (nc <= 0) continue;
+        cplx* L = Dfull + (size_t)c0 * ld;
+        cplx* R = Dfull + (size_t)(n + c0) * ld;
+        ZQ_NCCL_CHECK(g_nccl.Broadcast(L, L, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
+        ZQ_NCCL_CHECK(g_nccl.Broadcast(R, R, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
+      }
+      ZQ_NCCL_CHECK(g_nccl.GroupEnd());
+    }
     cudaEventRecord(p->ev[4], st);
   }
   cudaError_t e = cudaGetLastError();
@@ -265,7 +387,7 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   rc = get_plan(n, nb, &p);
   if (rc) return rc;
   if (devp) {
-    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, st);
+    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, opt ? opt->dist : 0, st);
     if (rc) return rc;
     if (opt && opt->sync) {
       int info = 0;
@@ -282,7 +404,7 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   cudaEventRecord(p->ev[0], st);
   ZQ_CUDA_CHECK(cudaMemcpy2DAsync(p->Dfull, ld * sizeof(cplx), D, (size_t)ld2 * sizeof(cplx), (size_t)n2 * sizeof(cplx),
                                   (size_t)n, cudaMemcpyHostToDevice, st));
-  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, st);
+  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, opt ? opt->dist : 0, st);
   if (rc) return rc;
   if (jobz)
     ZQ_CUDA_CHECK(cudaMemcpy2DAsync(D, (size_t)ld2 * sizeof(cplx), p->Dfull, ld * sizeof(cplx), (size_t)n2 * sizeof(cplx),
@@ -318,6 +440,37 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
     if (rc != 0 && worst == 0) worst = rc;
   }
   return worst;
+}
+
+int zquatev_b200_dist_unique_id(void* id128) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  ZQ_NCCL_CHECK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+int zquatev_b200_dist_init(int rank, int world, const void* id128) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = nccl_load();
+  if (rc) return rc;
+  if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+  if (world <= 1) { g_rank = 0; g_world = 1; return 0; }
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ZQ_NCCL_CHECK(g_nccl.CommInitRank(&g_comm, world, id, rank));
+  g_rank = rank;
+  g_world = world;
+  return 0;
+}
+
+void zquatev_b200_dist_finalize(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_comm) { cudaDeviceSynchronize(); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+  g_rank = 0;
+  g_world = 1;
 }
 
 void zquatev_b200_release(void) {

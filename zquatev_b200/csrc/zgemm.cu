@@ -70,7 +70,7 @@ struct OpTile {
 template <int BM, int BN, int BK, int STAGES, int TA, int TB>
 __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32)
 k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t lda, const cplx* __restrict__ B,
-            size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC) {
+            size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC, int cb0, int cbs) {
   constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
   using TileA = OpTile<BM, TA == 1, BK>;
   using TileB = OpTile<BN, TB == 0, BK>;
@@ -78,7 +78,7 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* smem = reinterpret_cast<cplx*>(smem_raw);
 
-  const int r0 = blockIdx.x * BM, c0 = blockIdx.y * BN;
+  const int r0 = blockIdx.x * BM, c0 = (cb0 + blockIdx.y * cbs) * BN;
   if (lower && r0 + BM - 1 < c0) return;
   A += (size_t)blockIdx.z * sA;
   B += (size_t)blockIdx.z * sB;
@@ -177,7 +177,7 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
 
 template <int BM, int BN, int BK, int STAGES, int TA, int TB>
 void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
-                size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st) {
+                size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
   using TileA = OpTile<BM, TA == 1, BK>;
   using TileB = OpTile<BN, TB == 0, BK>;
   constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
@@ -187,37 +187,45 @@ void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, cons
     cudaFuncSetAttribute(k_zgemm_mma<BM, BN, BK, STAGES, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  dim3 g((M + BM - 1) / BM, (N + BN - 1) / BN, batch);
-  k_zgemm_mma<BM, BN, BK, STAGES, TA, TB><<<g, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC);
+  dim3 g((M + BM - 1) / BM, ncb >= 0 ? ncb : (N + BN - 1) / BN, batch);
+  if (g.y == 0) return;
+  k_zgemm_mma<BM, BN, BK, STAGES, TA, TB><<<g, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC, cb0, cbs);
 }
 
 template <int TA, int TB>
 void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
-              size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, cudaStream_t st) {
+              size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
   // ZQ_GEMM_CFG (development knob): 0 auto, 1: 64x128 BK16 x3, 2: 64x64 BK16 x2 (2 CTAs/SM), 3: 64x64 BK8 x3
   static const int cfg_env = [] { const char* e = getenv("ZQ_GEMM_CFG"); return e ? atoi(e) : 0; }();
   int cfg = cfg_env;
+  if (ncb >= 0) cfg = 3;   // column-block addressing assumes BN = 64
   if (cfg == 0) {
     cfg = 3;   // measured best on every shape of the solver (profiles/r01_gemm_configs.md)
   }
   if (cfg == 1)
-    launch_cfg<64, 128, 16, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+    launch_cfg<64, 128, 16, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
   else if (cfg == 2)
-    launch_cfg<64, 64, 16, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+    launch_cfg<64, 64, 16, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
   else
-    launch_cfg<64, 64, 8, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+    launch_cfg<64, 64, 8, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
 }
 
 }  // namespace
 
+void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
+                     size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
+                     size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || batch <= 0) return;
+  if (ta == 0 && tb == 0) launch_t<0, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+  else if (ta == 0 && tb == 1) launch_t<0, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+  else if (ta == 1 && tb == 0) launch_t<1, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+  else launch_t<1, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+}
+
 void launch_zgemm(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
                   size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
                   size_t sC, cudaStream_t st) {
-  if (M <= 0 || N <= 0 || batch <= 0) return;
-  if (ta == 0 && tb == 0) launch_t<0, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
-  else if (ta == 0 && tb == 1) launch_t<0, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
-  else if (ta == 1 && tb == 0) launch_t<1, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
-  else launch_t<1, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, st);
+  launch_zgemm_cb(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, 0, 1, -1, st);
 }
 
 }  // namespace zq

@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed carries the 128-byte NCCL unique id,
+the C library owns the communicator used inside the solver."""
+from __future__ import annotations
+
+import ctypes
+
+from . import api
+
+
+def column_block(rank: int, world: int, n: int):
+    """Eigenvector column block [col0, col0 + ncols) that `rank` back-transforms (mirrors
+    solve_device in csrc/solver.cu): ceil(n / world) columns per rank, the last ranks may get fewer."""
+    per = (n + world - 1) // world
+    col0 = min(rank * per, n)
+    return col0, max(0, min(per, n - col0))
+
+
+def owner_of_column(k: int, world: int, nb: int = 64) -> int:
+    """Rank that owns column k of (D; E) in the 1-D block-cyclic layout of the reduction."""
+    return (k // nb) % world
+
+
+def exchange_unique_id(make_id, group=None):
+    """rank 0 calls `make_id()` -> 128 bytes; everyone receives them through torch.distributed
+    (works with the nccl and the gloo backend)."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        raw = make_id()
+        assert len(raw) == 128
+        buf = torch.tensor(list(raw), dtype=torch.uint8)
+    if dist.get_backend(group) == "nccl":
+        dev = buf.cuda()
+        dist.broadcast(dev, 0, group=group)
+        buf = dev.cpu()
+    else:
+        dist.broadcast(buf, 0, group=group)
+    return bytes(buf.tolist())
+
+
+def _make_nccl_id() -> bytes:
+    raw = (ctypes.c_ubyte * 128)()
+    rc = api.lib().zquatev_b200_dist_unique_id(raw)
+    if rc != 0:
+        raise RuntimeError(f"zquatev_b200_dist_unique_id failed: {rc}")
+    return bytes(raw)
+
+
+def init_from_torch(group=None):
+    """Creates the solver's NCCL communicator on the current CUDA device for all ranks of the
+    (already initialised) torch.distributed process group.  Returns (rank, world)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    raw = exchange_unique_id(_make_nccl_id, group)
+    buf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+    rc = api.lib().zquatev_b200_dist_init(rank, world, buf)
+    if rc != 0:
+        raise RuntimeError(f"zquatev_b200_dist_init failed: {rc}")
+    return rank, world
+
+
+def finalize():
+    api.lib().zquatev_b200_dist_finalize()
