@@ -277,7 +277,7 @@ def main():
                 host[:n].copy_(host0)
                 barrier()
                 t0 = time.perf_counter()
-                opt = z.ZqOptions(1, 0, args.nb, None, 1, 0, 0, 1 if world > 1 else 0)
+                opt = z.ZqOptions(1, 0, args.nb, None, 1, 0, 0, 1 if world > 1 else 0, 1)
                 info = z.lib().zquatev_b200_ex(n2, ctypes.c_void_p(host.data_ptr()), n2, eig_h.ctypes.data, ctypes.byref(opt))
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0
@@ -289,7 +289,7 @@ def main():
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e = {"value": te.item(), "unit": "s", "h2d_bytes_per_step": 16 * n2 * n, "d2h_bytes_per_step": 16 * n2 * n2 + 8 * n,
                    "phases_ms": z.last_phases(),
-                   "note": "host-pointer C ABI call zquatev_b200_ex (== ts::zquatev), pinned host array" + ("; every rank uploads its copy and downloads the full result" if world > 1 else "")}
+                   "note": "host-pointer C ABI call zquatev_b200_ex (== ts::zquatev), pinned host array" + ("; every rank uploads its copy of the input, rank 0 downloads all 2n columns, the others their own column blocks" if world > 1 else "")}
         except Exception as ex:   # e.g. not enough pinned host memory on the box
             e2e = {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
 
@@ -320,7 +320,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": f"2n={n2} quaternionic Hermitian eigendecomposition (values+vectors), G_sym seed 32",
                            "n2": n2, "nb": args.nb or 64, "l2": "inputs (16*n2*n B) larger than L2; fresh copy of the input every step",
-                           "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: reduction 1-D block-cyclic (64-column blocks) with per-column NCCL broadcast + all-reduce, D&C replicated, back-transform sharded by eigenvector columns, NCCL gather of the result"},
+                           "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: reduction 1-D block-cyclic (64-column blocks), per-column reflector broadcast + partial mat-vec all-reduce by " + ("peer-memory stores fused into the panel kernels (CUDA IPC over NVLink)" if z.lib().zquatev_b200_dist_transport() == 2 else "NCCL collectives") + ", D&C replicated, back-transform sharded by eigenvector columns, NCCL gather of the result"},
                 "tflops_canonical": 164.0 / 3.0 * n ** 3 / sec * 1e-12,
                 "phases_ms": phases, "trace_error": trace_err, "gpu_launches": launches, "clocks": clocks,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}

@@ -60,6 +60,10 @@ typedef struct zq_options {
                         D and E are treated as distributed 1-D block-cyclic by 64-column blocks, the
                         back-transformation is split by eigenvector columns, and on return every
                         rank holds the complete result.  Needs nb = 64.                           */
+  int host_result;   /* dist with host pointers: 0 = every rank downloads all 2n columns (default),
+                        1 = rank 0 downloads everything, rank r > 0 only its own eigenvector columns
+                        [r*ceil(n/G), ...) and their Kramers partners (the host links are shared by all
+                        GPUs of a box, so G full downloads cost G times one).                      */
 } zq_options;
 
 /* Same contract as zquatev_b200 plus options.  With jobz = 0 D is destroyed (holds reflectors). */
@@ -77,6 +81,10 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
 int zquatev_b200_dist_unique_id(void* id128);
 int zquatev_b200_dist_init(int rank, int world, const void* id128);
 void zquatev_b200_dist_finalize(void);
+/* 0: no communicator, 1: per-column NCCL broadcast + all-reduce, 2: fused peer-memory exchange (the
+ * panel kernels store into the peers' HBM over NVLink through CUDA-IPC mappings; NCCL only carries the
+ * final gather).  Transport 2 is chosen when every peer can be mapped; ZQ_DIST_NCCL=1 forces 1.       */
+int zquatev_b200_dist_transport(void);
 
 /* Workspace cache: plans (device workspaces for one n) are created on first use and cached per
  * thread-safe global table; this frees them.                                                  */

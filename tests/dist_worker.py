@@ -19,32 +19,36 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    zd.init_from_torch()
     world = dist.get_world_size()
     out = []
-    for n, seed in [(3, 1), (64, 2), (65, 3), (130, 4), (333, 5), (700, 6)]:
-        M = O.gen_sym(n, seed)
-        buf0 = torch.from_numpy(np.asfortranarray(M).T.copy()).cuda()     # column-major memory of M
-        res = {}
-        for mode in ("single", "dist"):
-            buf = buf0.clone()
-            eig = torch.zeros(n, dtype=torch.float64, device="cuda")
-            info = z.zquatev_device(2 * n, buf.data_ptr(), 2 * n, eig.data_ptr(), nb=64, dist=(mode == "dist"))
-            res[mode] = (info, eig.cpu().numpy(), buf.cpu().numpy().T.copy())
-        i0, e0, o0 = res["single"]
-        i1, e1, o1 = res["dist"]
-        nrm = np.abs(e0).max()
-        r1, q1, p1 = O.quality(M, o1, e1)
-        r0, q0, _ = O.quality(M, o0, e0)
-        # every rank must hold the same complete result
-        chk = torch.tensor([float(np.abs(o1).sum()), float(e1.sum())], dtype=torch.float64, device="cuda")
-        lst = [torch.zeros_like(chk) for _ in range(world)]
-        dist.all_gather(lst, chk)
-        same = all(torch.equal(lst[0], t) for t in lst)
-        ok = (i0 == 0 and i1 == 0 and np.max(np.abs(e0 - e1)) <= 1e-12 * nrm and p1 == 0.0
-              and r1 <= max(1.5 * r0, 0.6) and q1 <= max(1.5 * q0, 2.0) and same)
-        out.append({"n": n, "ok": bool(ok), "eig_dev": float(np.max(np.abs(e0 - e1)) / nrm), "res": r1, "res_single": r0,
-                    "orth": q1, "orth_single": q0, "pair": p1, "ranks_agree": bool(same)})
+    # pass 0: fused peer-memory exchange (CUDA IPC + NVLink stores); pass 1: NCCL per-column collectives
+    for transport in ("peer", "nccl"):
+      os.environ["ZQ_DIST_NCCL"] = "1" if transport == "nccl" else "0"
+      zd.init_from_torch()
+      for n, seed in [(3, 1), (64, 2), (65, 3), (130, 4), (333, 5), (700, 6)]:
+          M = O.gen_sym(n, seed)
+          buf0 = torch.from_numpy(np.asfortranarray(M).T.copy()).cuda()     # column-major memory of M
+          res = {}
+          for mode in ("single", "dist"):
+              buf = buf0.clone()
+              eig = torch.zeros(n, dtype=torch.float64, device="cuda")
+              info = z.zquatev_device(2 * n, buf.data_ptr(), 2 * n, eig.data_ptr(), nb=64, dist=(mode == "dist"))
+              res[mode] = (info, eig.cpu().numpy(), buf.cpu().numpy().T.copy())
+          i0, e0, o0 = res["single"]
+          i1, e1, o1 = res["dist"]
+          nrm = np.abs(e0).max()
+          r1, q1, p1 = O.quality(M, o1, e1)
+          r0, q0, _ = O.quality(M, o0, e0)
+          # every rank must hold the same complete result
+          chk = torch.tensor([float(np.abs(o1).sum()), float(e1.sum())], dtype=torch.float64, device="cuda")
+          lst = [torch.zeros_like(chk) for _ in range(world)]
+          dist.all_gather(lst, chk)
+          same = all(torch.equal(lst[0], t) for t in lst)
+          ok = (i0 == 0 and i1 == 0 and np.max(np.abs(e0 - e1)) <= 1e-12 * nrm and p1 == 0.0
+                and r1 <= max(1.5 * r0, 0.6) and q1 <= max(1.5 * q0, 2.0) and same)
+          out.append({"transport": transport, "n": n, "ok": bool(ok), "eig_dev": float(np.max(np.abs(e0 - e1)) / nrm), "res": r1, "res_single": r0,
+                      "orth": q1, "orth_single": q0, "pair": p1, "ranks_agree": bool(same)})
+    zd.finalize()
     if rank == 0:
         print("DIST_RESULT " + json.dumps(out), flush=True)
     zd.finalize()

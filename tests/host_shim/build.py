@@ -51,20 +51,22 @@ class HostCores:
                                      org.ctypes.data_as(P), mu.ctypes.data_as(P), it.ctypes.data_as(P))
         return org, mu, worst
 
-    def deflate(self, rho, ds, zs, col):
+    def deflate(self, rho, ds, zs, col, n1=None):
         nm = len(ds)
         ds = np.ascontiguousarray(ds, dtype=np.float64)
         zs = np.ascontiguousarray(zs, dtype=np.float64)
         col = np.ascontiguousarray(col, dtype=np.int32)
         dlam = np.zeros(nm); wz = np.zeros(nm); dfval = np.zeros(nm); rcc = np.zeros(nm); rss = np.zeros(nm)
-        ndcol = np.zeros(nm, dtype=np.int32); dfcol = np.zeros(nm, dtype=np.int32)
+        ndcol = np.zeros(nm, dtype=np.int32); dfcol = np.zeros(nm, dtype=np.int32); ndtype = np.zeros(nm, dtype=np.int32)
+        n1 = nm // 2 if n1 is None else n1
         rc1 = np.zeros(nm, dtype=np.int32); rc2 = np.zeros(nm, dtype=np.int32)
         out3 = np.zeros(3, dtype=np.int32)
         P = ctypes.c_void_p
         a = lambda x: x.ctypes.data_as(P)
-        self.lib.zqh_deflate(nm, ctypes.c_double(rho), a(ds), a(zs), a(col), a(dlam), a(wz), a(ndcol), a(dfval),
+        self.lib.zqh_deflate(nm, n1, ctypes.c_double(rho), a(ds), a(zs), a(col), a(dlam), a(wz), a(ndcol), a(ndtype), a(dfval),
                              a(dfcol), a(rc1), a(rc2), a(rcc), a(rss), a(out3))
         k, nd, nr = (int(v) for v in out3)
         assert k + nd == nm
+        self.last_types = ndtype[:k].copy()
         rots = [(int(rc1[i]), int(rc2[i]), float(rcc[i]), float(rss[i])) for i in range(nr)]
         return k, dlam[:k].copy(), wz[:k].copy(), ndcol[:k].copy(), dfval[:nd].copy(), dfcol[:nd].copy(), rots

@@ -13,9 +13,9 @@ int zqh_secular(int k, const double* dl, const double* z2, double rho, int* org,
   return worst;
 }
 int zqh_leaf(int m, double* d, double* e, double* Z, int ldz) { return leaf_ql<OneLane>(m, d, e, Z, ldz); }
-void zqh_deflate(int nm, double rho, const double* ds, const double* zs, const int* col, double* dlam, double* wz,
-                 int* ndcol, double* dfval, int* dfcol, int* rc1, int* rc2, double* rcc, double* rss, int* out3) {
-  DeflateOut o = deflate_scan<OneLane>(nm, rho, ds, zs, col, dlam, wz, ndcol, dfval, dfcol, rc1, rc2, rcc, rss);
+void zqh_deflate(int nm, int n1, double rho, const double* ds, const double* zs, const int* col, double* dlam, double* wz,
+                 int* ndcol, int* ndtype, double* dfval, int* dfcol, int* rc1, int* rc2, double* rcc, double* rss, int* out3) {
+  DeflateOut o = deflate_scan<OneLane>(nm, n1, rho, ds, zs, col, dlam, wz, ndcol, ndtype, dfval, dfcol, rc1, rc2, rcc, rss);
   out3[0] = o.k; out3[1] = o.ndefl; out3[2] = o.nrot;
 }
 }

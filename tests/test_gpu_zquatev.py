@@ -27,9 +27,9 @@ def check_quality(M, out, eig, g=None):
     else:
         # "at or below the reference's": both numbers are in units of N*eps, so for tiny matrices they
         # are a handful of roundings and move by O(1) with the BLAS build / summation order; the
-        # comparison therefore carries 15 % slack and, for n < 64 ONLY, the floors 0.6 (residual) /
-        # 2.0 (orthogonality); for n >= 64 there is no floor (at n = 200, 500 the reference has 0.048 / 1.02 and 0.027 / 0.92).
-        small = len(eig) < 64
+        # comparison therefore carries 15 % slack and, for n <= 64 ONLY, the floors 0.6 (residual) /
+        # 2.0 (orthogonality); for n > 64 there is no floor (at n = 200, 500 the reference has 0.048 / 1.02 and 0.027 / 0.92).
+        small = len(eig) <= 64
         assert res <= max(1.15 * g["residual"], 0.6 if small else 0.0), (res, g["residual"])
         assert orth <= max(1.15 * g["orthogonality"], 2.0 if small else 0.0), (orth, g["orthogonality"])
     return res, orth

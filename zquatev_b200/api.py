@@ -15,7 +15,7 @@ _lib = None
 class ZqOptions(ctypes.Structure):
     """struct zq_options of include/zquatev_b200.h"""
     _fields_ = [("jobz", ctypes.c_int), ("device_ptrs", ctypes.c_int), ("nb", ctypes.c_int),
-                ("stream", ctypes.c_void_p), ("sync", ctypes.c_int), ("col0", ctypes.c_int), ("ncols", ctypes.c_int), ("dist", ctypes.c_int)]
+                ("stream", ctypes.c_void_p), ("sync", ctypes.c_int), ("col0", ctypes.c_int), ("ncols", ctypes.c_int), ("dist", ctypes.c_int), ("host_result", ctypes.c_int)]
 
 
 # every symbol include/zquatev_b200.h declares: name -> (restype, argtypes)
@@ -28,6 +28,7 @@ SYMBOLS = {
     "zquatev_b200_dist_unique_id": (_I, [_P]),
     "zquatev_b200_dist_init": (_I, [_I, _I, _P]),
     "zquatev_b200_dist_finalize": (None, []),
+    "zquatev_b200_dist_transport": (_I, []),
     "zquatev_b200_last_phases": (_I, [_P]),
     "zquatev_b200_set_profiling": (None, [_I]),
     "zquatev_b200_version": (ctypes.c_char_p, []),
@@ -79,7 +80,7 @@ def zquatev(n2: int, D: np.ndarray, ld2: int, eig: np.ndarray, jobz: int = 1, nb
         raise ValueError("D must be contiguous")
     if D.size < ld2 * n2 or eig.size < n2 // 2:
         raise ValueError("D or eig too small")
-    opt = ZqOptions(jobz, 0, nb, None, 1, 0, 0, 0)
+    opt = ZqOptions(jobz, 0, nb, None, 1, 0, 0, 0, 0)
     info = lib().zquatev_b200_ex(n2, D.ctypes.data, ld2, eig.ctypes.data, ctypes.byref(opt))
     return _check(info, "zquatev")
 
@@ -88,7 +89,7 @@ def zquatev_device(n2: int, D_ptr: int, ld2: int, eig_ptr: int, jobz: int = 1, n
                    sync: bool = True, col0: int = 0, ncols: int = 0, dist: bool = False) -> int:
     """Device-resident variant: D_ptr / eig_ptr are CUDA device addresses (e.g. torch
     ``tensor.data_ptr()``) of a column-major ld2 x n2 complex128 array and n doubles."""
-    opt = ZqOptions(jobz, 1, nb, ctypes.c_void_p(stream) if stream else None, 1 if sync else 0, col0, ncols, 1 if dist else 0)
+    opt = ZqOptions(jobz, 1, nb, ctypes.c_void_p(stream) if stream else None, 1 if sync else 0, col0, ncols, 1 if dist else 0, 0)
     info = lib().zquatev_b200_ex(n2, ctypes.c_void_p(D_ptr), ld2, ctypes.c_void_p(eig_ptr), ctypes.byref(opt))
     return _check(info, "zquatev_device")
 

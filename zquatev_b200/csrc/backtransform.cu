@@ -135,6 +135,7 @@ void launch_phase_chain(int n, const quat* alpha, const double* e, quat* s, cuda
 
 void launch_scale_Z(int n, int ncols, const double* Z, size_t ldz, const int* perm, const quat* s, cplx* X, size_t ldx,
                     cudaStream_t st) {
+  if (ncols <= 0) return;
   dim3 g((n + 255) / 256, ncols);
   k_scale_Z<<<g, 256, 0, st>>>(n, Z, ldz, perm, s, X, ldx);
 }
@@ -145,6 +146,7 @@ void launch_pairing(int n, cplx* Out, size_t ld, cudaStream_t st) {
 }
 
 void launch_swap_pairing(int n, int ncols, cplx* Out, size_t ld, cudaStream_t st) {
+  if (ncols <= 0) return;
   dim3 g((n + 255) / 256, ncols);
   k_swap_pairing<<<g, 256, 0, st>>>(n, Out, ld);
 }

@@ -33,6 +33,7 @@ struct DcWs {
   double *z = nullptr, *ds = nullptr, *zs = nullptr, *dlam = nullptr, *wz = nullptr, *z2 = nullptr;
   double *dfval = nullptr, *rcc = nullptr, *rss = nullptr, *zhat = nullptr, *lam = nullptr, *rho = nullptr;
   int *col = nullptr, *ndcol = nullptr, *dfcol = nullptr, *rc1 = nullptr, *rc2 = nullptr, *kcnt = nullptr, *perm = nullptr;
+  int *ndtype = nullptr, *pinv = nullptr, *acol = nullptr;
   double* scale = nullptr;
   void* base = nullptr;
   long launches = 0;
@@ -41,6 +42,7 @@ struct DcWs {
 namespace {
 
 constexpr int GB = 64, GK = 16;
+constexpr int KC = 8;   // ints per merge in kcnt: k, ndefl, nrot, k1, k2 (columns of type 1 / 2), spare
 
 __global__ void __launch_bounds__(1024) k_dc_init(int n, const double* din, const double* ein, double* d, double* e,
                                                   double* scale) {
@@ -135,20 +137,46 @@ __global__ void __launch_bounds__(256) k_dc_prep(const MergeDesc* mg, const doub
 
 __global__ void __launch_bounds__(32) k_dc_deflate(const MergeDesc* mg, const double* rho, const double* ds,
                                                    const double* zs, const int* col, double* dlam, double* wz,
-                                                   double* z2, int* ndcol, double* dfval, int* dfcol, int* rc1,
-                                                   int* rc2, double* rcc, double* rss, int* kcnt) {
+                                                   double* z2, int* ndcol, int* ndtype, double* dfval, int* dfcol, int* rc1,
+                                                   int* rc2, double* rcc, double* rss, int* pinv, int* acol, int* kcnt) {
   const MergeDesc md = mg[blockIdx.x];
-  const int nm = md.n1 + md.n2, off = md.off;
-  DeflateOut o = deflate_scan<WarpLanes>(nm, rho[blockIdx.x], ds + off, zs + off, col + off, dlam + off, wz + off,
-                                         ndcol + off, dfval + off, dfcol + off, rc1 + off, rc2 + off, rcc + off,
-                                         rss + off);
+  const int nm = md.n1 + md.n2, off = md.off, lane = threadIdx.x;
+  DeflateOut o = deflate_scan<WarpLanes>(nm, md.n1, rho[blockIdx.x], ds + off, zs + off, col + off, dlam + off, wz + off,
+                                         ndcol + off, ndtype + off, dfval + off, dfcol + off, rc1 + off, rc2 + off,
+                                         rcc + off, rss + off);
   __syncwarp();
   __threadfence_block();
-  for (int i = threadIdx.x; i < o.k; i += 32) { const double v = wz[off + i]; z2[off + i] = v * v; }
-  if (threadIdx.x == 0) {
-    kcnt[3 * blockIdx.x + 0] = o.k;
-    kcnt[3 * blockIdx.x + 1] = o.ndefl;
-    kcnt[3 * blockIdx.x + 2] = o.nrot;
+  for (int i = lane; i < o.k; i += 32) { const double v = wz[off + i]; z2[off + i] = v * v; }
+  // rows of the secular eigenvector matrix S are stored grouped by column type [1 | 2 | 3] (stable), so
+  // the merge GEMM multiplies the rows of child 1 with S-rows [0, k1+k2) and those of child 2 with [k1, k)
+  int cnt[3] = {0, 0, 0};
+  for (int l0 = 0; l0 < o.k; l0 += 32) {
+    const int l = l0 + lane;
+    const int t = (l < o.k) ? ndtype[off + l] : 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cnt[c] += __popc(__ballot_sync(0xffffffffu, t == c + 1));
+  }
+  int base[3] = {0, cnt[0], cnt[0] + cnt[1]};
+  for (int l0 = 0; l0 < o.k; l0 += 32) {
+    const int l = l0 + lane;
+    const int t = (l < o.k) ? ndtype[off + l] : 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned m = __ballot_sync(0xffffffffu, t == c + 1);
+      if (t == c + 1) {
+        const int pos = base[c] + __popc(m & ((1u << lane) - 1u));
+        pinv[off + pos] = l;
+        acol[off + pos] = ndcol[off + l];
+      }
+      base[c] += __popc(m);
+    }
+  }
+  if (lane == 0) {
+    kcnt[KC * blockIdx.x + 0] = o.k;
+    kcnt[KC * blockIdx.x + 1] = o.ndefl;
+    kcnt[KC * blockIdx.x + 2] = o.nrot;
+    kcnt[KC * blockIdx.x + 3] = cnt[0];
+    kcnt[KC * blockIdx.x + 4] = cnt[1];
   }
 }
 
@@ -156,7 +184,7 @@ __global__ void __launch_bounds__(256) k_dc_rotate(const MergeDesc* mg, const in
                                                    const double* rcc, const double* rss, double* Q, size_t ldq) {
   const MergeDesc md = mg[blockIdx.y];
   const int nm = md.n1 + md.n2, off = md.off;
-  const int nrot = kcnt[3 * blockIdx.y + 2];
+  const int nrot = kcnt[KC * blockIdx.y + 2];
   const int r = blockIdx.x * 256 + threadIdx.x;
   if (r >= nm || nrot == 0) return;
   for (int q = 0; q < nrot; ++q) {
@@ -171,11 +199,11 @@ __global__ void __launch_bounds__(256) k_dc_rotate(const MergeDesc* mg, const in
 }
 
 __global__ void __launch_bounds__(256) k_dc_secular(const MergeDesc* mg, const int* kcnt, const double* rho,
-                                                    const double* dlam, const double* z2, double* S, size_t lds,
-                                                    double* lam, int* info) {
+                                                    const double* dlam, const double* z2, const int* __restrict__ pinv,
+                                                    double* S, size_t lds, double* lam, int* info) {
   const MergeDesc md = mg[blockIdx.y];
   const int off = md.off;
-  const int k = kcnt[3 * blockIdx.y];
+  const int k = kcnt[KC * blockIdx.y];
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j >= k) return;
   const int lane = threadIdx.x & 31;
@@ -184,7 +212,7 @@ __global__ void __launch_bounds__(256) k_dc_secular(const MergeDesc* mg, const i
   const int it = secular_root<WarpLanes>(j, k, dlam + off, z2 + off, rho[blockIdx.y], &org, &mu);
   const double dorg = dlam[off + org];
   double* Sc = S + (size_t)off + (size_t)(off + j) * lds;
-  for (int i = lane; i < k; i += 32) Sc[i] = (dlam[off + i] - dorg) - mu;
+  for (int r = lane; r < k; r += 32) Sc[r] = (dlam[off + pinv[off + r]] - dorg) - mu;   // S-row r <-> pole pinv[r]
   if (lane == 0) {
     lam[off + j] = dorg + mu;
     if (it >= 100) atomicOr(info, 2);
@@ -192,28 +220,29 @@ __global__ void __launch_bounds__(256) k_dc_secular(const MergeDesc* mg, const i
 }
 
 __global__ void __launch_bounds__(256) k_dc_zhat(const MergeDesc* mg, const int* kcnt, const double* __restrict__ dlam,
-                                                 const double* __restrict__ wz, const double* __restrict__ S, size_t lds,
-                                                 double* zhat) {
+                                                 const double* __restrict__ wz, const int* __restrict__ pinv,
+                                                 const double* __restrict__ S, size_t lds, double* zhat) {
   const MergeDesc md = mg[blockIdx.y];
   const int off = md.off;
-  const int k = kcnt[3 * blockIdx.y];
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= k) return;
+  const int k = kcnt[KC * blockIdx.y];
+  const int r = blockIdx.x * 256 + threadIdx.x;      // S-row
+  if (r >= k) return;
+  const int i = pinv[off + r];                       // its pole
   const double di = dlam[off + i];
-  const double* Sr = S + (size_t)(off + i) + (size_t)off * lds;
+  const double* Sr = S + (size_t)(off + r) + (size_t)off * lds;
   double p = Sr[(size_t)i * lds];
   for (int j = 0; j < k; ++j) {
     if (j == i) continue;
     p *= Sr[(size_t)j * lds] / (di - dlam[off + j]);
   }
-  zhat[off + i] = copysign(sqrt(fabs(p)), wz[off + i]);
+  zhat[off + r] = copysign(sqrt(fabs(p)), wz[off + i]);   // indexed by S-row
 }
 
 __global__ void __launch_bounds__(128) k_dc_vectors(const MergeDesc* mg, const int* kcnt, const double* __restrict__ zhat,
                                                     double* S, size_t lds) {
   const MergeDesc md = mg[blockIdx.y];
   const int off = md.off;
-  const int k = kcnt[3 * blockIdx.y];
+  const int k = kcnt[KC * blockIdx.y];
   const int j = blockIdx.x;
   if (j >= k) return;
   __shared__ double sm[32];
@@ -230,67 +259,106 @@ __global__ void __launch_bounds__(128) k_dc_vectors(const MergeDesc* mg, const i
   for (int i = threadIdx.x; i < k; i += 128) Sc[i] *= inv;
 }
 
-// Qnew[off + r, off + j] = sum_l Qold[off + r, off + ndcol[l]] * S[off + l, off + j]   (r < nm; j, l < k)
-__global__ void __launch_bounds__(256) k_dc_gemm(const MergeDesc* mg, const int* kcnt, const int* __restrict__ ndcol,
-                                                 const double* __restrict__ Qold, const double* __restrict__ S,
-                                                 double* __restrict__ Qnew, size_t ld) {
-  const MergeDesc md = mg[blockIdx.z];
-  const int nm = md.n1 + md.n2, off = md.off;
-  const int k = kcnt[3 * blockIdx.z];
-  const int r0 = blockIdx.x * GB, c0 = blockIdx.y * GB;
-  if (r0 >= nm || c0 >= k) return;
-  __shared__ double As[GK][GB + 1];
-  __shared__ double Bs[GK][GB + 1];
-  __shared__ int cidx[GK];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
+// Merge GEMM on the FP64 tensor path (DMMA m8n8k4), sizes read on the device:
+//   rows of child 1:  Qnew[off + r, off + j]      = sum_{p in [0, k1+k2)} Qold[off + r, off + acol[p]] * S[off + p, off + j]
+//   rows of child 2:  Qnew[off + n1 + r, off + j] = sum_{p in [k1, k)}     Qold[off + n1 + r, off + acol[p]] * S[off + p, off + j]
+// (the skipped products are exact zeros: a type-1 column vanishes in the rows of child 2 and vice versa).
+// CTA tile 128 x 128, 8 warps (4 x 2) of 32 x 64, BK = 16, 3-stage cp.async (8-byte) pipeline.
+constexpr int DG_BM = 128, DG_BN = 128, DG_BK = 16, DG_ST = 3, DG_LDA = DG_BM + 4, DG_LDB = DG_BK + 4;
+constexpr int DG_STAGE = DG_BK * DG_LDA + DG_BN * DG_LDB;   // doubles per stage
+
+ZQ_D void cp_async8(void* smem, const void* gmem, bool pred) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int sz = pred ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+
+__global__ void __launch_bounds__(256) k_dc_gemm_mma(const MergeDesc* mg, const int* kcnt, const int* __restrict__ acol,
+                                                     const double* __restrict__ Qold, const double* __restrict__ S,
+                                                     double* __restrict__ Qnew, size_t ld) {
+  const int merge = blockIdx.z >> 1, half = blockIdx.z & 1;
+  const MergeDesc md = mg[merge];
+  const int off = md.off;
+  const int k = kcnt[KC * merge], k1 = kcnt[KC * merge + 3], k2 = kcnt[KC * merge + 4];
+  const int rb = half ? md.n1 : 0, nr = half ? md.n2 : md.n1;
+  const int kb = half ? k1 : 0, KK = half ? (k - k1) : (k1 + k2);
+  const int r0 = blockIdx.x * DG_BM, c0 = blockIdx.y * DG_BN;
+  if (r0 >= nr || c0 >= k || KK <= 0) return;      // Qnew was zero-filled
+  extern __shared__ __align__(16) unsigned char dg_smem_raw[];
+  double* smem = reinterpret_cast<double*>(dg_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 64;
+  const int g = lane >> 2, q = lane & 3;
+  const double* Abase = Qold + (size_t)(off + rb + r0) + (size_t)off * ld;
+  const double* Bbase = S + (size_t)(off + kb) + (size_t)(off + c0) * ld;
+  const int* ac = acol + off + kb;
+
+  double acc[4][8][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k0 = 0; k0 < k; k0 += GK) {
-    __syncthreads();
-    if (tid < GK) cidx[tid] = (k0 + tid < k) ? ndcol[off + k0 + tid] : 0;
-    __syncthreads();
+    for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int nk = (KK + DG_BK - 1) / DG_BK;
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      double* sa = smem + (size_t)(kt % DG_ST) * DG_STAGE;
+      double* sb = sa + DG_BK * DG_LDA;
+      const int k0 = kt * DG_BK;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      {  // A: contiguous along rows
-        const int r = r0 + (tid & 63), kk = (tid >> 6) + 4 * q;
-        double v = 0.0;
-        if (r < nm && k0 + kk < k) v = Qold[(size_t)(off + r) + (size_t)(off + cidx[kk]) * ld];
-        As[kk][tid & 63] = v;
+      for (int e = tid; e < DG_BM * DG_BK; e += 256) {
+        const int m = e % DG_BM, kk = e / DG_BM;
+        const bool ok = (r0 + m < nr) && (k0 + kk < KK);
+        const double* src = ok ? Abase + m + (size_t)ac[k0 + kk] * ld : Qold;
+        cp_async8(sa + kk * DG_LDA + m, src, ok);
       }
-      {  // B: contiguous along l
-        const int kk = tid & 15, c = c0 + (tid >> 4) + 16 * q;
-        double v = 0.0;
-        if (c < k && k0 + kk < k) v = S[(size_t)(off + k0 + kk) + (size_t)(off + c) * ld];
-        Bs[kk][(tid >> 4) + 16 * q] = v;
+#pragma unroll
+      for (int e = tid; e < DG_BN * DG_BK; e += 256) {
+        const int kk = e % DG_BK, nn = e / DG_BK;
+        const bool ok = (c0 + nn < k) && (k0 + kk < KK);
+        const double* src = ok ? Bbase + (k0 + kk) + (size_t)nn * ld : S;
+        cp_async8(sb + nn * DG_LDB + kk, src, ok);
       }
     }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+#pragma unroll
+  for (int s2 = 0; s2 < DG_ST - 1; ++s2) issue(s2);
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(DG_ST - 2));
     __syncthreads();
+    issue(kt + DG_ST - 1);
+    const double* sa = smem + (size_t)(kt % DG_ST) * DG_STAGE;
+    const double* sb = sa + DG_BK * DG_LDA;
 #pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      double a[4], b[4];
+    for (int k4 = 0; k4 < DG_BK; k4 += 4) {
+      double a[4], b[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+      for (int i = 0; i < 4; ++i) a[i] = sa[(k4 + q) * DG_LDA + wm + 8 * i + g];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+      for (int j = 0; j < 8; ++j) b[j] = sb[(wn + 8 * j + g) * DG_LDB + k4 + q];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
     }
   }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  double* Cbase = Qnew + (size_t)(off + rb + r0) + (size_t)(off + c0) * ld;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = c0 + ty + 16 * j;
-    if (c >= k) continue;
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + tx + 16 * i;
-      if (r < nm) Qnew[(size_t)(off + r) + (size_t)(off + c) * ld] = acc[i][j];
+    for (int h = 0; h < 2; ++h) {
+      const int c = wn + 8 * j + 2 * q + h;
+      if (c0 + c >= k) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = wm + 8 * i + g;
+        if (r0 + r < nr) Cbase[(size_t)r + (size_t)c * ld] = acc[i][j][h];
+      }
     }
-  }
 }
 
 __global__ void __launch_bounds__(256) k_dc_finish(const MergeDesc* mg, const int* kcnt, const int* __restrict__ dfcol,
@@ -299,7 +367,7 @@ __global__ void __launch_bounds__(256) k_dc_finish(const MergeDesc* mg, const in
                                                    double* d) {
   const MergeDesc md = mg[blockIdx.z];
   const int nm = md.n1 + md.n2, off = md.off;
-  const int k = kcnt[3 * blockIdx.z];
+  const int k = kcnt[KC * blockIdx.z];
   const int c = blockIdx.y;            // column of the merged block
   const int r = blockIdx.x * 256 + threadIdx.x;
   if (c >= nm || (int)(blockIdx.x * 256) >= nm) return;
@@ -405,9 +473,9 @@ DcWs* dc_create(int n) {
   const size_t oQ0 = take(nn * 8), oQ1 = take(nn * 8), oS = take(nn * 8);
   size_t od[14];
   for (int i = 0; i < 14; ++i) od[i] = take(nd * 8);
-  size_t oi[6];
-  for (int i = 0; i < 6; ++i) oi[i] = take(nd * 4);
-  const size_t okc = take((size_t)nmerge_max * 3 * 4), orho = take((size_t)nmerge_max * 8);
+  size_t oi[9];
+  for (int i = 0; i < 9; ++i) oi[i] = take(nd * 4);
+  const size_t okc = take((size_t)nmerge_max * KC * 4), orho = take((size_t)nmerge_max * 8);
   const size_t omg = take(all.size() * sizeof(MergeDesc)), obd = take((bounds.size() + 1) * 4), osc = take(8);
   char* base = nullptr;
   if (cudaMalloc(&base, bytes) != cudaSuccess) { delete ws; return nullptr; }
@@ -417,8 +485,8 @@ DcWs* dc_create(int n) {
                      &ws->rss, &ws->zhat, &ws->lam, &ws->rho};
   for (int i = 0; i < 13; ++i) *dp[i] = (double*)(base + od[i]);
   ws->rho = (double*)(base + orho);
-  int** ip[6] = {&ws->col, &ws->ndcol, &ws->dfcol, &ws->rc1, &ws->rc2, &ws->perm};
-  for (int i = 0; i < 6; ++i) *ip[i] = (int*)(base + oi[i]);
+  int** ip[9] = {&ws->col, &ws->ndcol, &ws->dfcol, &ws->rc1, &ws->rc2, &ws->perm, &ws->ndtype, &ws->pinv, &ws->acol};
+  for (int i = 0; i < 9; ++i) *ip[i] = (int*)(base + oi[i]);
   ws->kcnt = (int*)(base + okc);
   ws->merges = (MergeDesc*)(base + omg);
   ws->bounds = (int*)(base + obd);
@@ -439,6 +507,11 @@ void dc_destroy(DcWs* ws) {
 int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, double** Zres, int** perm, int* info,
              cudaStream_t st) {
   const size_t ld = (size_t)n;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_dc_gemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DG_ST * DG_STAGE * sizeof(double)));
+    attr_done = true;
+  }
   k_dc_init<<<1, 1024, 0, st>>>(n, d, e, ws->d, ws->e, ws->scale);
   if (ws->nbounds > 0) k_dc_tear<<<cdiv(ws->nbounds, 128), 128, 0, st>>>(ws->nbounds, ws->bounds, ws->d, ws->e);
   cudaMemsetAsync(ws->Q[0], 0, (size_t)n * n * sizeof(double), st);
@@ -452,13 +525,17 @@ int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, do
     double* Qnew = ws->Q[cur ^ 1];
     cudaMemsetAsync(Qnew, 0, (size_t)n * n * sizeof(double), st);
     k_dc_prep<<<dim3(cdiv(L.maxnm, 256), L.count), 256, 0, st>>>(mg, ws->d, ws->e, Qold, ld, ws->ds, ws->zs, ws->col, ws->rho);
-    k_dc_deflate<<<L.count, 32, 0, st>>>(mg, ws->rho, ws->ds, ws->zs, ws->col, ws->dlam, ws->wz, ws->z2, ws->ndcol,
-                                         ws->dfval, ws->dfcol, ws->rc1, ws->rc2, ws->rcc, ws->rss, ws->kcnt);
+    k_dc_deflate<<<L.count, 32, 0, st>>>(mg, ws->rho, ws->ds, ws->zs, ws->col, ws->dlam, ws->wz, ws->z2, ws->ndcol, ws->ndtype,
+                                         ws->dfval, ws->dfcol, ws->rc1, ws->rc2, ws->rcc, ws->rss, ws->pinv, ws->acol, ws->kcnt);
     k_dc_rotate<<<dim3(cdiv(L.maxnm, 256), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->rc1, ws->rc2, ws->rcc, ws->rss, Qold, ld);
-    k_dc_secular<<<dim3(cdiv(L.maxnm, 8), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->rho, ws->dlam, ws->z2, ws->S, ld, ws->lam, info);
-    k_dc_zhat<<<dim3(cdiv(L.maxnm, 256), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dlam, ws->wz, ws->S, ld, ws->zhat);
+    k_dc_secular<<<dim3(cdiv(L.maxnm, 8), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->rho, ws->dlam, ws->z2, ws->pinv, ws->S, ld, ws->lam, info);
+    k_dc_zhat<<<dim3(cdiv(L.maxnm, 256), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dlam, ws->wz, ws->pinv, ws->S, ld, ws->zhat);
     k_dc_vectors<<<dim3(L.maxnm, L.count), 128, 0, st>>>(mg, ws->kcnt, ws->zhat, ws->S, ld);
-    k_dc_gemm<<<dim3(cdiv(L.maxnm, GB), cdiv(L.maxnm, GB), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->ndcol, Qold, ws->S, Qnew, ld);
+    {
+      const int n1max = (L.maxnm + 1) / 2;
+      k_dc_gemm_mma<<<dim3(cdiv(n1max, DG_BM), cdiv(L.maxnm, DG_BN), 2 * L.count), 256, DG_ST * DG_STAGE * sizeof(double), st>>>(
+          mg, ws->kcnt, ws->acol, Qold, ws->S, Qnew, ld);
+    }
     k_dc_finish<<<dim3(cdiv(L.maxnm, 256), L.maxnm, L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dfcol, ws->dfval, ws->lam, Qold, Qnew, ld, ws->d);
     cur ^= 1;
   }

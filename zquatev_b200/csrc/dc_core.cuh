@@ -207,15 +207,17 @@ ZQ_HD int leaf_ql(int m, double* d, double* e, double* Z, int ldz) {
 // ds[nm], zs[nm], col[nm] (original column of each sorted entry).  rho > 0.
 // Outputs: k and, for the k surviving entries in ascending order, dlam/wz/ndcol; for the nm-k
 // deflated entries dfval/dfcol; the list of plane rotations (rc1, rc2, rcs: c, s) to be
-// applied IN ORDER to the eigenvector columns.  Executed redundantly by every lane (state is
-// scalar); only lane 0 stores.
+// applied IN ORDER to the eigenvector columns.  ndtype[] classifies each surviving column like
+// dlaed2 does: 1 = non-zero only in the rows of child 1 (col < n1), 3 = only in the rows of child 2,
+// 2 = dense (a rotation mixed columns of both children) -- the merge GEMM skips the zero halves.
+// Executed redundantly by every lane (state is scalar); only lane 0 stores.
 // ---------------------------------------------------------------------------------------------
 struct DeflateOut { int k, ndefl, nrot; };
 
 template <class Lanes>
-ZQ_HD DeflateOut deflate_scan(int nm, double rho, const double* ds, const double* zs, const int* col, double* dlam,
-                              double* wz, int* ndcol, double* dfval, int* dfcol, int* rc1, int* rc2, double* rcc,
-                              double* rss) {
+ZQ_HD DeflateOut deflate_scan(int nm, int n1, double rho, const double* ds, const double* zs, const int* col, double* dlam,
+                              double* wz, int* ndcol, int* ndtype, double* dfval, int* dfcol, int* rc1, int* rc2,
+                              double* rcc, double* rss) {
   const int lane = Lanes::id(), nl = Lanes::count();
   double dmax = 0.0, zmax = 0.0;
   for (int i = lane; i < nm; i += nl) { dmax = fmax(dmax, fabs(ds[i])); zmax = fmax(zmax, fabs(zs[i])); }
@@ -231,7 +233,7 @@ ZQ_HD DeflateOut deflate_scan(int nm, double rho, const double* ds, const double
   }
   bool havep = false;
   double pd = 0.0, pz = 0.0;
-  int pc = 0;
+  int pc = 0, pt = 1;
   for (int j = 0; j < nm; ++j) {
     const double dj = ds[j], zj = zs[j];
     const int cj = col[j];
@@ -240,7 +242,8 @@ ZQ_HD DeflateOut deflate_scan(int nm, double rho, const double* ds, const double
       ++o.ndefl;
       continue;
     }
-    if (!havep) { havep = true; pd = dj; pz = zj; pc = cj; continue; }
+    const int tj = (cj < n1) ? 1 : 3;
+    if (!havep) { havep = true; pd = dj; pz = zj; pc = cj; pt = tj; continue; }
     double s = pz, c = zj;
     const double tau = hypot(c, s);
     const double t = dj - pd;
@@ -254,15 +257,15 @@ ZQ_HD DeflateOut deflate_scan(int nm, double rho, const double* ds, const double
       const double dcur = pd * s * s + dj * c * c;
       if (st) { dfval[o.ndefl] = dprev; dfcol[o.ndefl] = pc; }
       ++o.ndefl;
-      pd = dcur; pz = tau; pc = cj;
+      pd = dcur; pz = tau; pc = cj; pt = (pt == tj) ? pt : 2;
     } else {
-      if (st) { dlam[o.k] = pd; wz[o.k] = pz; ndcol[o.k] = pc; }
+      if (st) { dlam[o.k] = pd; wz[o.k] = pz; ndcol[o.k] = pc; ndtype[o.k] = pt; }
       ++o.k;
-      pd = dj; pz = zj; pc = cj;
+      pd = dj; pz = zj; pc = cj; pt = tj;
     }
   }
   if (havep) {
-    if (st) { dlam[o.k] = pd; wz[o.k] = pz; ndcol[o.k] = pc; }
+    if (st) { dlam[o.k] = pd; wz[o.k] = pz; ndcol[o.k] = pc; ndtype[o.k] = pt; }
     ++o.k;
   }
   return o;

@@ -37,6 +37,21 @@ struct PanelWs {
   int rank, world;
 };
 
+// Peer-memory exchange for the multi-GPU reduction (one process per GPU, buffers opened through
+// CUDA IPC, NVLink/NVSwitch stores): the two per-column collectives -- broadcast of the reflector,
+// all-reduce of the partial mat-vec -- are done by the panel kernels themselves with direct peer
+// stores and sequence-number flags instead of NCCL calls between kernels.
+constexpr int PX_MAXW = 8;
+struct PeerX {
+  int rank, world;
+  size_t nmax;                              // capacity (quaternions per vector)
+  quat* bvq[PX_MAXW];                       // [g]: rank g's landing zone for the reflector, nmax + 2 quats
+  quat* ypart[PX_MAXW];                     // [g]: rank g's staging [2 parities][world][nmax]
+  unsigned long long* flags[PX_MAXW];       // [g]: rank g's flags: [0] reflector seq, [8 + 8*parity + src] partial-y seq
+  unsigned int* counters;                   // local CTA arrival counters [2]
+  int* info;                                // local status word (bit 8 = exchange timeout)
+};
+
 // K2/K3 panel column kernels (panel.cu)
 void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st);
 void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st);
@@ -48,6 +63,14 @@ void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
 // after the broadcast of vq[k+1 .. n+2) from the owner of column k: store v into the panel, the
 // reflector storage of A and the scalars d,e,tau,alpha (vq[n] = (d,e,tau,0), vq[n+1] = alpha)
 void launch_unpack_v(const PanelWs& w, int k, int j0, cudaStream_t st);
+// peer-exchange variants (seq = monotonically increasing sequence number of this column):
+//   owner: reflector + push of v to every peer + flag;  others: wait for the flag, unpack
+void launch_reflector_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
+void launch_wait_unpack_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
+//   partial M v of the owned column blocks pushed into every rank's staging slot + flag
+void launch_reduce_partial_px(const PanelWs& w, const PeerX& px, int k, unsigned long long seq, cudaStream_t st);
+//   wait for all slots, sum them in rank order (bit-identical on every rank), correct, scale
+void launch_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
 void launch_finish_w(const PanelWs& w, int k_last, int j0, cudaStream_t st);
 // K1 quaternion-Hermitian mat-vec on the lower triangles (+ fused panel dot products)
 void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st);

@@ -44,6 +44,43 @@ ZQ_D quat warps_sum(quat v, quat (*sm)[PR], int warp, int lane) {
   return s;
 }
 
+// ---- peer-exchange primitives (multi-GPU) ----------------------------------------------------
+ZQ_D unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+ZQ_D void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+ZQ_D quat ldcg_quat(const quat* p) {      // data written by a peer GPU: read at L2, never from a stale L1 line
+  const double2* q = reinterpret_cast<const double2*>(p);
+  return qmake(__ldcg(q), __ldcg(q + 1));
+}
+// thread 0 of the CTA waits (bounded) until *flag >= seq
+ZQ_D void px_wait(const unsigned long long* flag, unsigned long long seq, int* info) {
+  if (*(volatile int*)info & 8) return;                                  // exchange already failed: do not wait again
+  const long long t0 = clock64();
+  while (ld_acquire_sys(flag) < seq) {
+    if (clock64() - t0 > 8000000000LL) { atomicOr(info, 8); break; }   // ~4 s: report instead of hanging the GPU
+    __nanosleep(64);
+  }
+}
+// every thread of the CTA has issued its peer stores; once ALL CTAs of the grid have, publish seq
+ZQ_D void px_signal(const PeerX& px, unsigned int* counter, int flag_index, unsigned long long seq, bool include_self) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *(volatile unsigned int*)counter = 0u;
+      __threadfence_system();
+      for (int g = 0; g < px.world; ++g)
+        if (include_self || g != px.rank) st_release_sys(px.flags[g] + flag_index, seq);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // col_update: rows r in [k, n)
 // ---------------------------------------------------------------------------------------------
@@ -119,7 +156,8 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
 // ---------------------------------------------------------------------------------------------
 // reflector: rows r in [k+1, n), 256 rows per CTA
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_reflector(PanelWs w, int k, int j0, int nparts) {
+template <bool PX>
+__global__ void __launch_bounds__(NT) k_reflector(PanelWs w, PeerX px, int k, int j0, int nparts, unsigned long long seq) {
   const int n = w.n, i = k - j0;
   const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
   __shared__ double s_red[32];
@@ -152,23 +190,41 @@ __global__ void __launch_bounds__(NT) k_reflector(PanelWs w, int k, int j0, int 
     pan_ptr(w, 0, i)[r] = v.a;
     pan_ptr(w, 1, i)[r] = v.b;
     w.vq[r] = v;
+    if (PX) {
+      for (int g = 0; g < px.world; ++g)
+        if (g != px.rank) px.bvq[g][r] = v;           // NVLink peer store
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     w.alpha[k] = alpha;
     w.e[k] = nx;
     w.tau[k] = tau;
     // scalars of this column ride behind the reflector in the broadcast buffer (multi-GPU)
-    w.vq[n] = qmake(cmake(w.d[k], nx), cmake(tau, 0.0));
+    const quat sc = qmake(cmake(w.d[k], nx), cmake(tau, 0.0));
+    w.vq[n] = sc;
     w.vq[n + 1] = alpha;
+    if (PX) {
+      for (int g = 0; g < px.world; ++g)
+        if (g != px.rank) { px.bvq[g][px.nmax] = sc; px.bvq[g][px.nmax + 1] = alpha; }
+    }
   }
+  if (PX) px_signal(px, px.counters + 0, 0, seq, false);
 }
 
 // multi-GPU: vq[k+1 .. n+2) has just been broadcast from the owner of column k
-__global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, int k, int j0) {
+template <bool PX>
+__global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, PeerX px, int k, int j0, unsigned long long seq) {
   const int n = w.n, i = k - j0;
   const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
+  const quat* src = PX ? px.bvq[px.rank] : w.vq;
+  const size_t sc_at = PX ? px.nmax : (size_t)n;
+  if (PX) {
+    if (threadIdx.x == 0) px_wait(px.flags[px.rank] + 0, seq, px.info);
+    __syncthreads();
+  }
   if (r < n) {
-    const quat v = w.vq[r];
+    const quat v = PX ? ldcg_quat(src + r) : src[r];
+    if (PX) w.vq[r] = v;
     pan_ptr(w, 0, i)[r] = v.a;
     pan_ptr(w, 1, i)[r] = v.b;
     if (r >= k + 2) {
@@ -177,11 +233,11 @@ __global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, int k, int j0) {
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const quat sc = w.vq[n];
+    const quat sc = PX ? ldcg_quat(src + sc_at) : src[sc_at];
     w.d[k] = sc.a.x;
     w.e[k] = sc.a.y;
     w.tau[k] = sc.b.x;
-    w.alpha[k] = w.vq[n + 1];
+    w.alpha[k] = PX ? ldcg_quat(src + sc_at + 1) : src[sc_at + 1];
     w.vq[k] = qzero();
   }
 }
@@ -191,14 +247,20 @@ __global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, int k, int j0) {
 // ---------------------------------------------------------------------------------------------
 // MODE 0: single GPU (sum all K1 partials, correct, scale).  MODE 1: multi-GPU, local part only:
 // w.p[r] = sum of THIS rank's partials.  MODE 2: multi-GPU, after the all-reduce of w.p: correct, scale.
+// MODE 3 / 4: as 1 / 2 with the peer exchange: 3 pushes the local part into slot [rank] of every rank's
+// staging buffer and signals; 4 waits for all slots and sums them in rank order.
 template <int MODE>
-__global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0, int nch) {
+__global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int k, int j0, int nch, unsigned long long seq) {
+  constexpr bool PART = (MODE == 1 || MODE == 3), FIN = (MODE == 2 || MODE == 4);
   const int n = w.n, i = k - j0, s = k + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = s + blockIdx.x * PR + lane;
   __shared__ quat gW[MAX_NB_PANEL], gV[MAX_NB_PANEL];
   __shared__ quat red[NW][PR];
-  if (MODE != 1) {
+  if (MODE == 4) {
+    if (threadIdx.x < px.world) px_wait(px.flags[px.rank] + 8 + 8 * (k & 1) + threadIdx.x, seq, px.info);
+  }
+  if (!PART) {
     for (int t = threadIdx.x; t < 2 * i; t += NT) {
       const int tt = t >> 1;
       const quat* src = (t & 1) ? w.dotV : w.dotW;
@@ -213,7 +275,7 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0,
   }
   quat part = qzero();
   if (r < n) {
-    if (MODE != 2) {
+    if (!FIN) {
       const int J0 = s / MV_TC, Jlast = (n - 1) / MV_TC;
       const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
       const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
@@ -224,9 +286,14 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0,
       if ((r / MV_TC) % w.world == w.rank)     // transposed sums exist only on the owner of r's column block
         for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
     } else if (warp == 0) {
-      part = w.p[r];                           // all-reduced M v
+      if (MODE == 2) {
+        part = w.p[r];                         // all-reduced M v (NCCL)
+      } else {                                 // sum the G staged partials in rank order
+        const quat* yp = px.ypart[px.rank] + (size_t)(k & 1) * px.world * px.nmax;
+        for (int g = 0; g < px.world; ++g) part = qadd(part, ldcg_quat(yp + (size_t)g * px.nmax + r));
+      }
     }
-    if (MODE != 1) {
+    if (!PART) {
       for (int t = warp; t < i; t += NW) {
         quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
         quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
@@ -238,6 +305,14 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, int k, int j0,
   quat y = warps_sum(part, red, warp, lane);
   if (MODE == 1) {
     if (warp == 0 && r < n) w.p[r] = y;
+    return;
+  }
+  if (MODE == 3) {
+    if (warp == 0 && r < n) {
+      const size_t at = ((size_t)(k & 1) * px.world + px.rank) * px.nmax + r;
+      for (int g = 0; g < px.world; ++g) px.ypart[g][at] = y;        // own slot on every rank (NVLink stores)
+    }
+    px_signal(px, px.counters + 1, 8 + 8 * (k & 1) + px.rank, seq, true);
     return;
   }
   if (warp == 0) {
@@ -307,29 +382,49 @@ void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st) {
 void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nparts = cdiv(w.n - k, PR);        // nrm_part written by col_update (rows k..n-1)
-  k_reflector<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, nparts);
+  k_reflector<false><<<cdiv(rows, NT), NT, 0, st>>>(w, PeerX{}, k, j0, nparts, 0ull);
 }
 
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nch = cdiv(rows, DOT_ROWS);
-  k_reduce_correct<0><<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, nch);
+  k_reduce_correct<0><<<cdiv(rows, PR), NT, 0, st>>>(w, PeerX{}, k, j0, nch, 0ull);
 }
 
 void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_reduce_correct<1><<<cdiv(rows, PR), NT, 0, st>>>(w, k, k, 0);
+  k_reduce_correct<1><<<cdiv(rows, PR), NT, 0, st>>>(w, PeerX{}, k, k, 0, 0ull);
 }
 
 void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nch = cdiv(rows, DOT_ROWS);
-  k_reduce_correct<2><<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, nch);
+  k_reduce_correct<2><<<cdiv(rows, PR), NT, 0, st>>>(w, PeerX{}, k, j0, nch, 0ull);
 }
 
 void launch_unpack_v(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_unpack_v<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0);
+  k_unpack_v<false><<<cdiv(rows, NT), NT, 0, st>>>(w, PeerX{}, k, j0, 0ull);
+}
+
+void launch_reflector_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  k_reflector<true><<<cdiv(rows, NT), NT, 0, st>>>(w, px, k, j0, cdiv(w.n - k, PR), seq);
+}
+
+void launch_wait_unpack_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  k_unpack_v<true><<<cdiv(rows, NT), NT, 0, st>>>(w, px, k, j0, seq);
+}
+
+void launch_reduce_partial_px(const PanelWs& w, const PeerX& px, int k, unsigned long long seq, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  k_reduce_correct<3><<<cdiv(rows, PR), NT, 0, st>>>(w, px, k, k, 0, seq);
+}
+
+void launch_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
+  const int rows = w.n - k - 1;
+  k_reduce_correct<4><<<cdiv(rows, PR), NT, 0, st>>>(w, px, k, j0, cdiv(rows, DOT_ROWS), seq);
 }
 
 void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {

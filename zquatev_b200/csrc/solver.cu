@@ -54,6 +54,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -61,6 +62,11 @@ struct NcclApi {
 static NcclApi g_nccl;
 static ncclComm_t g_comm = nullptr;
 static int g_rank = 0, g_world = 1;
+// peer-memory exchange state (CUDA IPC); g_px.world == 0: not available -> NCCL per-column collectives
+static PeerX g_px{};
+static char* g_xb = nullptr;                       // this rank's exchange buffer
+static void* g_peer_base[PX_MAXW] = {};
+static unsigned long long g_seq_base = 0;          // sequence numbers never restart (flags are never reset)
 
 static int nccl_load() {
   if (g_nccl.h) return 0;
@@ -70,7 +76,7 @@ static int nccl_load() {
 #define ZQ_SYM(field, name) *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) { fprintf(stderr, "[zquatev_b200] missing %s\n", name); return -901; }
   ZQ_SYM(GetUniqueId, "ncclGetUniqueId") ZQ_SYM(CommInitRank, "ncclCommInitRank") ZQ_SYM(CommDestroy, "ncclCommDestroy")
   ZQ_SYM(Broadcast, "ncclBroadcast") ZQ_SYM(AllReduce, "ncclAllReduce") ZQ_SYM(GroupStart, "ncclGroupStart")
-  ZQ_SYM(GroupEnd, "ncclGroupEnd") ZQ_SYM(GetErrorString, "ncclGetErrorString")
+  ZQ_SYM(GroupEnd, "ncclGroupEnd") ZQ_SYM(AllGather, "ncclAllGather") ZQ_SYM(GetErrorString, "ncclGetErrorString")
 #undef ZQ_SYM
   g_nccl.h = h;
   return 0;
@@ -192,6 +198,70 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
   p->launches += 1;
 }
 
+// Exchange-buffer layout per rank: [bvq: nmax+2 quats][ypart: 2*PX_MAXW*nmax quats][flags: 64 u64][counters: 16 u32]
+static size_t px_bytes(size_t nmax) { return ((nmax + 2) + 2 * (size_t)PX_MAXW * nmax) * sizeof(quat) + 64 * 8 + 16 * 4; }
+
+static void px_fill(PeerX& px, int g, char* base, size_t nmax) {
+  px.bvq[g] = (quat*)base;
+  px.ypart[g] = (quat*)base + (nmax + 2);
+  px.flags[g] = (unsigned long long*)((quat*)base + (nmax + 2) + 2 * (size_t)PX_MAXW * nmax);
+}
+
+static void px_teardown() {
+  for (int g = 0; g < PX_MAXW; ++g)
+    if (g_peer_base[g]) { cudaIpcCloseMemHandle(g_peer_base[g]); g_peer_base[g] = nullptr; }
+  if (g_xb) { cudaFree(g_xb); g_xb = nullptr; }
+  g_px = PeerX{};
+}
+
+// every rank allocates its buffer, the CUDA IPC handles are all-gathered over NCCL, peers are mapped
+static int px_setup(int rank, int world, size_t nmax) {
+  px_teardown();
+  if (world > PX_MAXW) return 0;                   // fall back to NCCL collectives
+  const char* off = getenv("ZQ_DIST_NCCL");
+  if (off && atoi(off) != 0) return 0;
+  const size_t bytes = px_bytes(nmax);
+  if (cudaMalloc(&g_xb, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaMemset(g_xb, 0, bytes);
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, g_xb) != cudaSuccess) { cudaGetLastError(); px_teardown(); return 0; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  char* dbuf = nullptr;
+  ZQ_CUDA_CHECK(cudaMalloc(&dbuf, 64 * (size_t)world));
+  ZQ_CUDA_CHECK(cudaMemcpy(dbuf + 64 * rank, &mine, 64, cudaMemcpyHostToDevice));
+  ZQ_NCCL_CHECK(g_nccl.AllGather(dbuf + 64 * rank, dbuf, 64, ncclChar, g_comm, 0));
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(0));
+  std::vector<cudaIpcMemHandle_t> all(world);
+  ZQ_CUDA_CHECK(cudaMemcpy(all.data(), dbuf, 64 * (size_t)world, cudaMemcpyDeviceToHost));
+  cudaFree(dbuf);
+  PeerX px{};
+  px.rank = rank; px.world = world; px.nmax = nmax;
+  int ok = 1;
+  for (int g = 0; g < world; ++g) {
+    char* base = g_xb;
+    if (g != rank) {
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      g_peer_base[g] = ptr;
+      base = (char*)ptr;
+    }
+    px_fill(px, g, base, nmax);
+  }
+  // all ranks must agree (a rank that cannot map its peers forces everyone onto the NCCL path)
+  int* dflag = nullptr;
+  ZQ_CUDA_CHECK(cudaMalloc(&dflag, sizeof(int)));
+  ZQ_CUDA_CHECK(cudaMemcpy(dflag, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  ZQ_NCCL_CHECK(g_nccl.AllReduce(dflag, dflag, 1, ncclInt, ncclMin, g_comm, 0));
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(0));
+  ZQ_CUDA_CHECK(cudaMemcpy(&ok, dflag, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dflag);
+  if (!ok) { px_teardown(); return 0; }
+  px.counters = (unsigned int*)((char*)px.flags[rank] + 64 * 8);
+  g_px = px;
+  g_seq_base = 0;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU reduction: D and E are distributed 1-D block-cyclic by 64-column blocks
 // (every rank keeps the full array but only its own blocks are kept up to date).  Per column: the
@@ -211,6 +281,9 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   }
   w.rank = g_rank;
   w.world = G;
+  const bool use_px = g_px.world == G && (size_t)n <= g_px.nmax;
+  PeerX px = g_px;
+  px.info = p->info_dev;
   cudaMemsetAsync(w.vq, 0, (size_t)(n + 2) * sizeof(quat), st);
   cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
@@ -221,16 +294,29 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
     for (int i = 0; i < kb; ++i) {
       const int k = j0 + i, m = n - k - 1;
       launch_col_update(w, k, j0, st);
-      if (owner == g_rank) launch_reflector(w, k, j0, st);
-      ZQ_NCCL_CHECK(g_nccl.Broadcast(w.vq + k + 1, w.vq + k + 1, (size_t)4 * (m + 2), ncclDouble, owner, g_comm, st));
-      launch_unpack_v(w, k, j0, st);
-      if (prof) cudaEventRecord(p->k1ev[2 * k], st);
-      launch_matvec(w, k, j0, st);
-      if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
-      launch_reduce_partial(w, k, st);
-      ZQ_NCCL_CHECK(g_nccl.AllReduce(w.p + k + 1, w.p + k + 1, (size_t)4 * m, ncclDouble, ncclSum, g_comm, st));
-      launch_correct(w, k, j0, st);
-      p->launches += 7;
+      if (use_px) {
+        // fused exchange: the kernels push v / the partial products straight into the peers' HBM over NVLink
+        const unsigned long long seq = g_seq_base + (unsigned long long)k + 1ull;
+        if (owner == g_rank) launch_reflector_px(w, px, k, j0, seq, st);
+        else launch_wait_unpack_px(w, px, k, j0, seq, st);
+        if (prof) cudaEventRecord(p->k1ev[2 * k], st);
+        launch_matvec(w, k, j0, st);
+        if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
+        launch_reduce_partial_px(w, px, k, seq, st);
+        launch_correct_px(w, px, k, j0, seq, st);
+        p->launches += 5;
+      } else {
+        if (owner == g_rank) launch_reflector(w, k, j0, st);
+        ZQ_NCCL_CHECK(g_nccl.Broadcast(w.vq + k + 1, w.vq + k + 1, (size_t)4 * (m + 2), ncclDouble, owner, g_comm, st));
+        launch_unpack_v(w, k, j0, st);
+        if (prof) cudaEventRecord(p->k1ev[2 * k], st);
+        launch_matvec(w, k, j0, st);
+        if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
+        launch_reduce_partial(w, k, st);
+        ZQ_NCCL_CHECK(g_nccl.AllReduce(w.p + k + 1, w.p + k + 1, (size_t)4 * m, ncclDouble, ncclSum, g_comm, st));
+        launch_correct(w, k, j0, st);
+        p->launches += 7;
+      }
     }
     launch_finish_w(w, j0 + kb - 1, j0, st);
     const int r0 = j0 + kb, m = n - r0;
@@ -248,6 +334,7 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   launch_col_update(w, n - 1, n - 1, st);          // d[n-1]: valid on the owner of the last column block
   ZQ_NCCL_CHECK(g_nccl.Broadcast(w.d + n - 1, w.d + n - 1, 1, ncclDouble, ((n - 1) / nb) % G, g_comm, st));
   p->launches += 1;
+  if (use_px) g_seq_base += (unsigned long long)n + 8ull;
   w.rank = 0;
   w.world = 1;
   return 0;
@@ -283,7 +370,7 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
 }
 
 // full solve on device-resident operands.  Dfull: 2n x 2n complex (ld), left half = input.
-static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, int dist, cudaStream_t st) {
+static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, int dist, int gather, cudaStream_t st) {
   const int n = p->n;
   PanelWs& w = p->pw;
   w.A = Dfull;
@@ -325,18 +412,26 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     launch_scale_Z(n, ncols, Z, (size_t)n, perm + col0, p->s, X + (size_t)col0 * ld, ld, st);
     backtransform(p, X + (size_t)col0 * ld, ld, ncols, st);
     launch_swap_pairing(n, ncols, Dfull + (size_t)col0 * ld, ld, st);
-    if (dist) {                                 // every rank ends with all 2n columns
+    if (dist && gather) {                       // every rank ends with all 2n columns
       const int per = (n + g_world - 1) / g_world;
-      ZQ_NCCL_CHECK(g_nccl.GroupStart());
-      for (int r = 0; r < g_world; ++r) {
-        const int c0 = r * per < n ? r * per : n, nc = (c0 + per <= n) ? per : n - c0;
-        if (nc <= 0) continue;
-        cplx* L = Dfull + (size_t)c0 * ld;
-        cplx* R = Dfull + (size_t)(n + c0) * ld;
-        ZQ_NCCL_CHECK(g_nccl.Broadcast(L, L, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
-        ZQ_NCCL_CHECK(g_nccl.Broadcast(R, R, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
+      if (n % g_world == 0) {                   // equal blocks: in-place all-gather of each half
+        cplx* L = Dfull;
+        cplx* R = Dfull + (size_t)n * ld;
+        const size_t cnt = (size_t)2 * per * ld;
+        ZQ_NCCL_CHECK(g_nccl.AllGather(L + (size_t)g_rank * per * ld, L, cnt, ncclDouble, g_comm, st));
+        ZQ_NCCL_CHECK(g_nccl.AllGather(R + (size_t)g_rank * per * ld, R, cnt, ncclDouble, g_comm, st));
+      } else {
+        ZQ_NCCL_CHECK(g_nccl.GroupStart());
+        for (int r = 0; r < g_world; ++r) {
+          const int c0 = r * per < n ? r * per : n, nc = (c0 + per <= n) ? per : n - c0;
+          if (nc <= 0) continue;
+          cplx* L = Dfull + (size_t)c0 * ld;
+          cplx* R = Dfull + (size_t)(n + c0) * ld;
+          ZQ_NCCL_CHECK(g_nccl.Broadcast(L, L, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
+          ZQ_NCCL_CHECK(g_nccl.Broadcast(R, R, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
+        }
+        ZQ_NCCL_CHECK(g_nccl.GroupEnd());
       }
-      ZQ_NCCL_CHECK(g_nccl.GroupEnd());
     }
     cudaEventRecord(p->ev[4], st);
   }
@@ -387,7 +482,7 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   rc = get_plan(n, nb, &p);
   if (rc) return rc;
   if (devp) {
-    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, opt ? opt->dist : 0, st);
+    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, opt ? opt->dist : 0, 1, st);
     if (rc) return rc;
     if (opt && opt->sync) {
       int info = 0;
@@ -404,11 +499,25 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   cudaEventRecord(p->ev[0], st);
   ZQ_CUDA_CHECK(cudaMemcpy2DAsync(p->Dfull, ld * sizeof(cplx), D, (size_t)ld2 * sizeof(cplx), (size_t)n2 * sizeof(cplx),
                                   (size_t)n, cudaMemcpyHostToDevice, st));
-  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, opt ? opt->dist : 0, st);
+  const int dist = opt ? opt->dist : 0;
+  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, dist, 1, st);
   if (rc) return rc;
-  if (jobz)
-    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(D, (size_t)ld2 * sizeof(cplx), p->Dfull, ld * sizeof(cplx), (size_t)n2 * sizeof(cplx),
-                                    (size_t)n2, cudaMemcpyDeviceToHost, st));
+  if (jobz) {
+    if (dist && opt->host_result == 1 && g_rank != 0) {
+      // distributed host result: this rank downloads only its own eigenvector columns (and their Kramers partners)
+      const int per = (n + g_world - 1) / g_world;
+      const int c0 = g_rank * per < n ? g_rank * per : n, nc = (c0 + per <= n) ? per : n - c0;
+      if (nc > 0) {
+        ZQ_CUDA_CHECK(cudaMemcpy2DAsync((cplx*)D + (size_t)c0 * ld2, (size_t)ld2 * sizeof(cplx), p->Dfull + (size_t)c0 * ld, ld * sizeof(cplx),
+                                        (size_t)n2 * sizeof(cplx), (size_t)nc, cudaMemcpyDeviceToHost, st));
+        ZQ_CUDA_CHECK(cudaMemcpy2DAsync((cplx*)D + (size_t)(n + c0) * ld2, (size_t)ld2 * sizeof(cplx), p->Dfull + (size_t)(n + c0) * ld,
+                                        ld * sizeof(cplx), (size_t)n2 * sizeof(cplx), (size_t)nc, cudaMemcpyDeviceToHost, st));
+      }
+    } else {
+      ZQ_CUDA_CHECK(cudaMemcpy2DAsync(D, (size_t)ld2 * sizeof(cplx), p->Dfull, ld * sizeof(cplx), (size_t)n2 * sizeof(cplx),
+                                      (size_t)n2, cudaMemcpyDeviceToHost, st));
+    }
+  }
   ZQ_CUDA_CHECK(cudaMemcpyAsync(eig, p->eig_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
   int info = 0;
   ZQ_CUDA_CHECK(cudaMemcpyAsync(&info, p->info_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -456,19 +565,22 @@ int zquatev_b200_dist_init(int rank, int world, const void* id128) {
   std::lock_guard<std::mutex> lk(g_mu);
   int rc = nccl_load();
   if (rc) return rc;
-  if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+  if (g_comm) { px_teardown(); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
   if (world <= 1) { g_rank = 0; g_world = 1; return 0; }
   ncclUniqueId id;
   memcpy(&id, id128, 128);
   ZQ_NCCL_CHECK(g_nccl.CommInitRank(&g_comm, world, id, rank));
   g_rank = rank;
   g_world = world;
-  return 0;
+  const char* nm = getenv("ZQ_PX_NMAX");
+  return px_setup(rank, world, nm ? (size_t)atol(nm) : (size_t)32768);
 }
+
+int zquatev_b200_dist_transport(void) { return g_comm ? (g_px.world == g_world ? 2 : 1) : 0; }
 
 void zquatev_b200_dist_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_comm) { cudaDeviceSynchronize(); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
+  if (g_comm) { cudaDeviceSynchronize(); px_teardown(); g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
   g_rank = 0;
   g_world = 1;
 }
