@@ -323,7 +323,16 @@ def main():
                            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: reduction 1-D block-cyclic (64-column blocks), per-column reflector broadcast + partial mat-vec all-reduce by " + ("peer-memory stores fused into the panel kernels (CUDA IPC over NVLink)" if z.lib().zquatev_b200_dist_transport() == 2 else "NCCL collectives") + ", D&C replicated, back-transform sharded by eigenvector columns, NCCL gather of the result"},
                 "tflops_canonical": 164.0 / 3.0 * n ** 3 / sec * 1e-12,
                 "phases_ms": phases, "trace_error": trace_err, "gpu_launches": launches, "clocks": clocks,
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e}
+                "roofline": roof,
+                # second roofline (FP64 tensor path): executed GEMM flops of the back-transformation (32 n^3 / N per rank)
+                # over its CUDA-event time; peak = DMMA rate measured on this pool with tools/fp64_peak.cu
+                "roofline_fp64": {"kernel": "k_zgemm_mma (K6 back-transformation, DMMA m8n8k4)", "bound": "tensor",
+                                  "achieved": 32.0 * n ** 3 / world / (phases["backtransform"] * 1e-3) * 1e-12 if phases["backtransform"] else None,
+                                  "peak": 37.1, "unit": "TFLOP/s",
+                                  "frac": 32.0 * n ** 3 / world / (phases["backtransform"] * 1e-3) * 1e-12 / 37.1 if phases["backtransform"] else None,
+                                  "peak_source": "own measurement (profiles/r01_fp64_peak.jsonl: DMMA 37.1, DFMA 36.9 TFLOP/s); MEASURED_PEAKS.json has no FP64 entry",
+                                  "note": "phase time includes operand staging, T factors, pairing and (N > 1) the NCCL gather"},
+                "cpu_baseline": cpu, "e2e": e2e}
         print(json.dumps(line), flush=True)
     if world > 1:
         from zquatev_b200 import dist as zd

@@ -275,14 +275,15 @@ ZQ_D void cp_async8(void* smem, const void* gmem, bool pred) {
 
 __global__ void __launch_bounds__(256) k_dc_gemm_mma(const MergeDesc* mg, const int* kcnt, const int* __restrict__ acol,
                                                      const double* __restrict__ Qold, const double* __restrict__ S,
-                                                     double* __restrict__ Qnew, size_t ld) {
+                                                     double* __restrict__ Qnew, size_t ld, int cbeg, int cend) {
   const int merge = blockIdx.z >> 1, half = blockIdx.z & 1;
   const MergeDesc md = mg[merge];
   const int off = md.off;
-  const int k = kcnt[KC * merge], k1 = kcnt[KC * merge + 3], k2 = kcnt[KC * merge + 4];
+  const int kfull = kcnt[KC * merge], k1 = kcnt[KC * merge + 3], k2 = kcnt[KC * merge + 4];
+  const int k = kfull < cend ? kfull : cend;          // columns [cbeg, min(k, cend)) belong to this rank (multi-GPU top merge)
   const int rb = half ? md.n1 : 0, nr = half ? md.n2 : md.n1;
-  const int kb = half ? k1 : 0, KK = half ? (k - k1) : (k1 + k2);
-  const int r0 = blockIdx.x * DG_BM, c0 = blockIdx.y * DG_BN;
+  const int kb = half ? k1 : 0, KK = half ? (kfull - k1) : (k1 + k2);
+  const int r0 = blockIdx.x * DG_BM, c0 = cbeg + blockIdx.y * DG_BN;
   if (r0 >= nr || c0 >= k || KK <= 0) return;      // Qnew was zero-filled
   extern __shared__ __align__(16) unsigned char dg_smem_raw[];
   double* smem = reinterpret_cast<double*>(dg_smem_raw);
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(256) k_dc_gemm_mma(const MergeDesc* mg, const 
 __global__ void __launch_bounds__(256) k_dc_finish(const MergeDesc* mg, const int* kcnt, const int* __restrict__ dfcol,
                                                    const double* __restrict__ dfval, const double* __restrict__ lam,
                                                    const double* __restrict__ Qold, double* __restrict__ Qnew, size_t ld,
-                                                   double* d) {
+                                                   double* d, int cbeg, int cend) {
   const MergeDesc md = mg[blockIdx.z];
   const int nm = md.n1 + md.n2, off = md.off;
   const int k = kcnt[KC * blockIdx.z];
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256) k_dc_finish(const MergeDesc* mg, const in
     return;
   }
   const int src = dfcol[off + c - k];
-  if (r < nm) Qnew[(size_t)(off + r) + (size_t)(off + c) * ld] = Qold[(size_t)(off + r) + (size_t)(off + src) * ld];
+  if (r < nm && c >= cbeg && c < cend) Qnew[(size_t)(off + r) + (size_t)(off + c) * ld] = Qold[(size_t)(off + r) + (size_t)(off + src) * ld];
   if (r == 0) d[off + c] = dfval[off + c - k];
 }
 
@@ -505,7 +506,7 @@ void dc_destroy(DcWs* ws) {
 }
 
 int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, double** Zres, int** perm, int* info,
-             cudaStream_t st) {
+             cudaStream_t st, const DcDist* dd) {
   const size_t ld = (size_t)n;
   static bool attr_done = false;
   if (!attr_done) {
@@ -532,11 +533,22 @@ int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, do
     k_dc_zhat<<<dim3(cdiv(L.maxnm, 256), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dlam, ws->wz, ws->pinv, ws->S, ld, ws->zhat);
     k_dc_vectors<<<dim3(L.maxnm, L.count), 128, 0, st>>>(mg, ws->kcnt, ws->zhat, ws->S, ld);
     {
+      // multi-GPU: the top merge (the block is the whole matrix, columns contiguous) is split by column
+      // blocks of the new eigenvector matrix and all-gathered; lower levels are replicated
+      const bool split = dd && dd->world > 1 && L.count == 1 && L.maxnm == n && n % dd->world == 0 && n >= 2048;
+      const int cbeg = split ? dd->rank * (n / dd->world) : 0;
+      const int cend = split ? cbeg + n / dd->world : 0x7fffffff;
+      const int ncolsg = split ? n / dd->world : L.maxnm;
       const int n1max = (L.maxnm + 1) / 2;
-      k_dc_gemm_mma<<<dim3(cdiv(n1max, DG_BM), cdiv(L.maxnm, DG_BN), 2 * L.count), 256, DG_ST * DG_STAGE * sizeof(double), st>>>(
-          mg, ws->kcnt, ws->acol, Qold, ws->S, Qnew, ld);
+      k_dc_gemm_mma<<<dim3(cdiv(n1max, DG_BM), cdiv(ncolsg, DG_BN), 2 * L.count), 256, DG_ST * DG_STAGE * sizeof(double), st>>>(
+          mg, ws->kcnt, ws->acol, Qold, ws->S, Qnew, ld, cbeg, cend);
+      k_dc_finish<<<dim3(cdiv(L.maxnm, 256), L.maxnm, L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dfcol, ws->dfval, ws->lam, Qold, Qnew,
+                                                                            ld, ws->d, cbeg, cend);
+      if (split) {
+        const int rc = dd->allgather(Qnew, (size_t)(n / dd->world) * n, dd->rank, st);
+        if (rc) return rc;
+      }
     }
-    k_dc_finish<<<dim3(cdiv(L.maxnm, 256), L.maxnm, L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dfcol, ws->dfval, ws->lam, Qold, Qnew, ld, ws->d);
     cur ^= 1;
   }
   k_dc_final_sort<<<cdiv(n, 256), 256, 0, st>>>(n, ws->d, ws->scale, wout, ws->perm);

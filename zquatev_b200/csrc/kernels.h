@@ -115,8 +115,11 @@ size_t dc_bytes(int n);
 long dc_launches(const DcWs* ws);
 // returns 0 / cuda error; eigenvalues (ascending) -> wout[n]; eigenvectors: column j of the result is
 // column perm[j] of Zres (pointer returned in *Zres, ld n).  info flag on device: *info_dev != 0 -> failure.
+// multi-GPU: the top-level merge GEMM is split by eigenvector column blocks; `allgather(buf, count, rank, st)`
+// gathers `count` doubles per rank in place (buf + rank*count is this rank's part)
+struct DcDist { int rank, world; int (*allgather)(double* buf, size_t count, int rank, cudaStream_t st); };
 int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, double** Zres, int** perm,
-             int* info_dev, cudaStream_t st);
+             int* info_dev, cudaStream_t st, const DcDist* dd = nullptr);
 
 // K9 eigenvalues only: Sturm bisection
 // scratch: n + 3 doubles

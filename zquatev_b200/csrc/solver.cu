@@ -398,7 +398,11 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     }
     double* Z = nullptr;
     int* perm = nullptr;
-    int rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st);
+    DcDist dd{g_rank, g_world, [](double* buf, size_t count, int rank, cudaStream_t s2) -> int {
+                ncclResult_t r = g_nccl.AllGather(buf + (size_t)rank * count, buf, count, ncclDouble, g_comm, s2);
+                return r == ncclSuccess ? 0 : nccl_fail(r, __LINE__);
+              }};
+    int rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st, dist ? &dd : nullptr);
     if (rc) return rc;
     p->launches += dc_launches(p->dc) + 3;
     cudaEventRecord(p->ev[3], st);
@@ -497,8 +501,12 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   const size_t ld = (size_t)n2;
   if (!p->Dfull) ZQ_CUDA_CHECK(cudaMalloc(&p->Dfull, ld * n2 * sizeof(cplx)));
   cudaEventRecord(p->ev[0], st);
-  ZQ_CUDA_CHECK(cudaMemcpy2DAsync(p->Dfull, ld * sizeof(cplx), D, (size_t)ld2 * sizeof(cplx), (size_t)n2 * sizeof(cplx),
-                                  (size_t)n, cudaMemcpyHostToDevice, st));
+  const int dist_in = opt ? opt->dist : 0;
+  if (!dist_in || g_rank == 0 || !g_comm)
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(p->Dfull, ld * sizeof(cplx), D, (size_t)ld2 * sizeof(cplx), (size_t)n2 * sizeof(cplx),
+                                    (size_t)n, cudaMemcpyHostToDevice, st));
+  if (dist_in && g_comm)     // the ranks share the host links: rank 0 uploads once, NVLink carries the input to the others
+    ZQ_NCCL_CHECK(g_nccl.Broadcast(p->Dfull, p->Dfull, (size_t)2 * n * ld, ncclDouble, 0, g_comm, st));
   const int dist = opt ? opt->dist : 0;
   rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, dist, 1, st);
   if (rc) return rc;
@@ -539,14 +547,76 @@ int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt
   return solve_any(n2, D, ld2, eig, opt);
 }
 
+// Batched small problems (BASELINE config 5): the problems are independent, so they are pipelined
+// over LANES concurrent CUDA streams, each with its own plan (workspace) -- H2D of problem b+LANES
+// overlaps the kernels of problems b+1.., and the latency-bound kernels of different problems share
+// the GPU.  (The reference has no batched entry: its callers loop over zquatev().)
 int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig, long long strideEig,
                          int* info) {
   if (batch < 0) return -1;
+  if (batch == 0) return 0;
+  int rc = check_args(n2, D, ld2, eig);
+  if (rc) return rc;
+  if (n2 == 0) return 0;
+  const int n = n2 / 2;
+  constexpr int LANES = 8;
+  std::lock_guard<std::mutex> lk(g_mu);
+  struct Lane { Plan* p = nullptr; cudaStream_t st = nullptr; int* hinfo = nullptr; cplx* hbuf = nullptr; double* heig = nullptr; };
+  static std::vector<Lane> lanes;
+  static int lanes_n = -1;
+  const int nl = batch < LANES ? batch : LANES;
+  if (lanes_n != n || (int)lanes.size() < nl) {
+    for (auto& L : lanes) { if (L.p) { cudaStreamSynchronize(L.st); plan_free(L.p); } if (L.st) cudaStreamDestroy(L.st); if (L.hinfo) cudaFreeHost(L.hinfo); if (L.hbuf) cudaFreeHost(L.hbuf); if (L.heig) cudaFreeHost(L.heig); }
+    lanes.assign(nl, Lane());
+    for (auto& L : lanes) {
+      rc = plan_create(n, DEFAULT_NB, &L.p);
+      if (rc) return rc;
+      ZQ_CUDA_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+      ZQ_CUDA_CHECK(cudaMalloc(&L.p->Dfull, (size_t)n2 * n2 * sizeof(cplx)));
+      ZQ_CUDA_CHECK(cudaMallocHost(&L.hinfo, sizeof(int) * 4));
+      // pinned staging: a D2H copy into pageable memory would block the host and serialise the lanes
+      ZQ_CUDA_CHECK(cudaMallocHost(&L.hbuf, (size_t)n2 * n2 * sizeof(cplx)));
+      ZQ_CUDA_CHECK(cudaMallocHost(&L.heig, (size_t)n * sizeof(double)));
+    }
+    lanes_n = n;
+  }
+  const size_t ld = (size_t)n2;
   int worst = 0;
+  std::vector<int> pending(nl, -1);            // problem whose info sits in the lane's pinned word
+  auto harvest = [&](int l) {
+    if (pending[l] < 0) return 0;
+    cudaError_t e = cudaStreamSynchronize(lanes[l].st);
+    if (e != cudaSuccess) return zq_cuda_fail(e, __FILE__, __LINE__);
+    const int v = lanes[l].hinfo[0];
+    {   // pinned staging -> caller's arrays
+      const int pb = pending[l];
+      cplx* Dp = (cplx*)D + (size_t)pb * strideD;
+      for (int c = 0; c < n2; ++c) memcpy(Dp + (size_t)c * ld2, lanes[l].hbuf + (size_t)c * n2, (size_t)n2 * sizeof(cplx));
+      memcpy(eig + (size_t)pb * strideEig, lanes[l].heig, (size_t)n * sizeof(double));
+    }
+    if (info) info[pending[l]] = v;
+    if (v != 0 && worst == 0) worst = v;
+    pending[l] = -1;
+    return 0;
+  };
   for (int b = 0; b < batch; ++b) {
-    const int rc = solve_any(n2, (cplx*)D + (size_t)b * strideD, ld2, eig + (size_t)b * strideEig, nullptr);
-    if (info) info[b] = rc;
-    if (rc != 0 && worst == 0) worst = rc;
+    const int l = b % nl;
+    Lane& L = lanes[l];
+    rc = harvest(l);
+    if (rc) return rc;
+    cplx* Db = (cplx*)D + (size_t)b * strideD;
+    for (int c = 0; c < n; ++c) memcpy(L.hbuf + (size_t)c * n2, Db + (size_t)c * ld2, (size_t)n2 * sizeof(cplx));
+    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.p->Dfull, L.hbuf, (size_t)n * n2 * sizeof(cplx), cudaMemcpyHostToDevice, L.st));
+    rc = solve_device(L.p, L.p->Dfull, ld, L.p->eig_dev, 1, 0, 0, 0, 0, L.st);
+    if (rc) return rc;
+    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.hbuf, L.p->Dfull, (size_t)n2 * n2 * sizeof(cplx), cudaMemcpyDeviceToHost, L.st));
+    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.heig, L.p->eig_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, L.st));
+    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.hinfo, L.p->info_dev, sizeof(int), cudaMemcpyDeviceToHost, L.st));
+    pending[l] = b;
+  }
+  for (int l = 0; l < nl; ++l) {
+    rc = harvest(l);
+    if (rc) return rc;
   }
   return worst;
 }
