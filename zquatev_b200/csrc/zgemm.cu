@@ -175,6 +175,136 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3M variant: a complex product from THREE real DMMAs instead of four,
+//   T1 = Ar Br,  T2 = Ai Bi,  T3 = (Ar + Ai)(Br + Bi);   Re = T1 - T2,  Im = T3 - T1 - T2,
+// i.e. 25 % fewer tensor-pipe cycles for the same result -- the same trade the reference makes by
+// calling zgemm3m everywhere (Makefile:2, f77.h:80-83).  The fragment sums are formed in registers;
+// three accumulator sets are kept, so the warp tile is 32 x 16 (CTA 64 x 32, 4 warps, 3 CTAs/SM).
+// Column-block addressing (multi-GPU trailing update): an owned 64-column block = two 32-column tiles.
+// ---------------------------------------------------------------------------------------------
+template <int BK, int STAGES, int TA, int TB>
+__global__ void __launch_bounds__(128)
+k_zgemm_3m(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t lda, const cplx* __restrict__ B,
+           size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC, int cb0, int cbs) {
+  constexpr int BM = 64, BN = 32, NTHREADS = 128;
+  using TileA = OpTile<BM, TA == 1, BK>;
+  using TileB = OpTile<BN, TB == 0, BK>;
+  constexpr int STAGE_ELEMS = TileA::ELEMS + TileB::ELEMS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+
+  const int r0 = blockIdx.x * BM;
+  const int c0 = (cb0 + (blockIdx.y >> 1) * cbs) * 64 + (blockIdx.y & 1) * BN;
+  if (c0 >= N || (lower && r0 + BM - 1 < c0)) return;
+  A += (size_t)blockIdx.z * sA;
+  B += (size_t)blockIdx.z * sB;
+  C += (size_t)blockIdx.z * sC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  const int g = lane >> 2, q = lane & 3;
+
+  const bool bzero = (beta.x == 0.0 && beta.y == 0.0);
+  if (!bzero) {
+    for (int e = tid; e < BN * (BM / 8); e += NTHREADS) {
+      const int c = c0 + e / (BM / 8), r = r0 + (e % (BM / 8)) * 8;
+      if (c < N && r < M) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(C + (size_t)r + (size_t)c * ldc));
+    }
+  }
+
+  double t1[4][2][2], t2[4][2][2], t3[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) t1[i][j][h] = t2[i][j][h] = t3[i][j][h] = 0.0;
+
+  const int nk = (K + BK - 1) / BK;
+  auto issue = [&](int kt) {
+    if (kt < nk) {
+      cplx* sa = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
+      cplx* sb = sa + TileA::ELEMS;
+      TileA::template load<NTHREADS>(sa, A, lda, r0, kt * BK, M, K, tid);
+      TileB::template load<NTHREADS>(sb, B, ldb, c0, kt * BK, N, K, tid);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(kt + STAGES - 1);
+    const cplx* sa = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
+    const cplx* sb = sa + TileA::ELEMS;
+#pragma unroll
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      double ar[4], ai[4], as[4], br[2], bi[2], bs[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const cplx a = TileA::frag(sa, wm + 8 * i + g, k4 + q);
+        ar[i] = a.x;
+        ai[i] = TA ? -a.y : a.y;
+        as[i] = ar[i] + ai[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const cplx b = TileB::frag(sb, wn + 8 * j + g, k4 + q);
+        br[j] = b.x;
+        bi[j] = TB ? -b.y : b.y;
+        bs[j] = br[j] + bi[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          dmma(t1[i][j][0], t1[i][j][1], ar[i], br[j]);
+          dmma(t2[i][j][0], t2[i][j][1], ai[i], bi[j]);
+          dmma(t3[i][j][0], t3[i][j][1], as[i], bs[j]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + wn + 8 * j + 2 * q + h;
+      if (c >= N) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + wm + 8 * i + g;
+        if (r >= M || (lower && r < c)) continue;
+        const double re = t1[i][j][h] - t2[i][j][h];
+        const double im = (t3[i][j][h] - t1[i][j][h]) - t2[i][j][h];
+        cplx v = cmul(alpha, cmake(re, im));
+        cplx* cp = C + (size_t)r + (size_t)c * ldc;
+        if (!bzero) { const cplx o = *cp; cfma(v, beta, o); }
+        *cp = v;
+      }
+    }
+}
+
+template <int TA, int TB>
+void launch_3m(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
+               size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
+  constexpr int BK = 8, STAGES = 3;
+  using TileA = OpTile<64, TA == 1, BK>;
+  using TileB = OpTile<32, TB == 0, BK>;
+  const size_t smem = (size_t)STAGES * (TileA::ELEMS + TileB::ELEMS) * sizeof(cplx);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_zgemm_3m<BK, STAGES, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  dim3 g((M + 63) / 64, ncb >= 0 ? 2 * ncb : 2 * ((N + 63) / 64), batch);
+  if (g.y == 0) return;
+  k_zgemm_3m<BK, STAGES, TA, TB><<<g, 128, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC, cb0, cbs);
+}
+
 template <int BM, int BN, int BK, int STAGES, int TA, int TB>
 void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
                 size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
@@ -197,6 +327,12 @@ void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const 
               size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
   // ZQ_GEMM_CFG (development knob): 0 auto, 1: 64x128 BK16 x3, 2: 64x64 BK16 x2 (2 CTAs/SM), 3: 64x64 BK8 x3
   static const int cfg_env = [] { const char* e = getenv("ZQ_GEMM_CFG"); return e ? atoi(e) : 0; }();
+  // ZQ_GEMM_3M: 1 (default) = three-multiplication complex product (k_zgemm_3m), 0 = conventional four
+  static const int use_3m = [] { const char* e = getenv("ZQ_GEMM_3M"); return e ? atoi(e) : 1; }();
+  if (use_3m && cfg_env == 0) {
+    launch_3m<TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+    return;
+  }
   int cfg = cfg_env;
   if (ncb >= 0) cfg = 3;   // column-block addressing assumes BN = 64
   if (cfg == 0) {
