@@ -1,4 +1,5 @@
-"""Launches the two dominant kernels once at headline-workload shapes (for `ncu --set full`):
+"""(timings printed here are meaningless under ncu)
+Launches the two dominant kernels once at headline-workload shapes (for `ncu --set full`):
 K1 mat-vec on a 16384^2 trailing matrix and the DMMA GEMM at the trailing-update / back-transform
 shapes of 2n = 32768 (nb = 64)."""
 import ctypes, os, sys

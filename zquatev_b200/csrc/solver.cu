@@ -156,6 +156,40 @@ static int get_plan(int n, int nb, Plan** out) {
   return rc;
 }
 
+// The panel (V_a,V_b,W_a,W_b: 4*nb*n complex, 67 MB at n = 16384) is re-read by col_update, the dot CTAs and
+// reduce_correct of EVERY column while K1 streams gigabytes through the L2 in between.  An access-policy window
+// can pin it in the 126 MB L2 (hitProp = persisting) for the duration of the reduction.  Measured on B200 at
+// 2n = 32768 it is SLOWER (tridiagonalisation 6.43 -> 6.65 s: K1 loses streaming capacity), so it is off by
+// default; ZQ_L2_PERSIST=1 enables it.
+static void l2_window(cudaStream_t st, void* base, size_t bytes) {
+  static const int on = [] { const char* e = getenv("ZQ_L2_PERSIST"); return e ? atoi(e) : 0; }();
+  if (!on) return;
+  static size_t max_win = 0, max_persist = 0;
+  static bool init = false;
+  if (!init) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) {
+      max_win = (size_t)pr.accessPolicyMaxWindowSize;
+      max_persist = (size_t)pr.persistingL2CacheMaxSize;
+      if (max_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, max_persist);
+    }
+    cudaGetLastError();
+    init = true;
+  }
+  if (!max_win || !max_persist) return;
+  cudaStreamAttrValue v{};
+  v.accessPolicyWindow.base_ptr = base;
+  v.accessPolicyWindow.num_bytes = bytes < max_win ? bytes : max_win;
+  v.accessPolicyWindow.hitRatio = bytes <= max_persist ? 1.0f : (float)((double)max_persist / (double)bytes);
+  v.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+  if (!bytes) cudaCtxResetPersistingL2Cache();
+  cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1-K4: reduction of (D; E) to a quaternion tridiagonal, reflectors left in the lower triangles
 // ---------------------------------------------------------------------------------------------
@@ -166,6 +200,7 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
   cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
+  if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
   const bool prof = g_profile;
   if (prof && p->k1ev.size() < 2 * (size_t)n) {
     const size_t old = p->k1ev.size();
@@ -196,6 +231,7 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
   }
   launch_col_update(w, n - 1, n - 1, st);   // d[n-1]
   p->launches += 1;
+  if (n >= 2048) l2_window(st, w.pan, 0);
 }
 
 // Exchange-buffer layout per rank: [bvq: nmax+2 quats][ypart: 2*PX_MAXW*nmax quats][flags: 64 u64][counters: 16 u32]
@@ -282,6 +318,7 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   w.rank = g_rank;
   w.world = G;
   const bool use_px = g_px.world == G && (size_t)n <= g_px.nmax;
+  if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
   PeerX px = g_px;
   px.info = p->info_dev;
   cudaMemsetAsync(w.vq, 0, (size_t)(n + 2) * sizeof(quat), st);
@@ -335,6 +372,7 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   ZQ_NCCL_CHECK(g_nccl.Broadcast(w.d + n - 1, w.d + n - 1, 1, ncclDouble, ((n - 1) / nb) % G, g_comm, st));
   p->launches += 1;
   if (use_px) g_seq_base += (unsigned long long)n + 8ull;
+  if (n >= 2048) l2_window(st, w.pan, 0);
   w.rank = 0;
   w.world = 1;
   return 0;
