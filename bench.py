@@ -100,6 +100,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def traffic_probe():
+    """dram bytes of ONE K1 launch from the committed ncu --set full capture (the step average over 16383 launches of
+    shrinking size is not capturable under ncu; `traffic` itself therefore stays null)"""
+    p = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -254,7 +264,7 @@ def main():
         ach = alg_bytes / (k1_ms * 1e-3) * 1e-9 if k1_ms > 0 else None
         roof = {"kernel": "k_matvec (K1 quaternion-Hermitian mat-vec, lower triangles)", "bound": "hbm",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
-                "traffic": None, "peak_source": src, "launches": n - 1, "k1_ms_per_step": k1_ms,
+                "traffic": None, "traffic_probe": traffic_probe(), "peak_source": src, "launches": n - 1, "k1_ms_per_step": k1_ms,
                 "share_of_step": k1_ms / ph["device_total"] if ph["device_total"] else None,
                 "algorithmic_bytes_per_step": alg_bytes,
                 "note": "algorithmic bytes = 16 m^2 per column (lower triangles only; SURVEY 8d's full-storage figure is 32 m^2)"}

@@ -87,6 +87,10 @@ void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStr
 void launch_zgemm(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
                   size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
                   size_t sC, cudaStream_t st);
+// 3M complex product (three real DMMA products per complex product, as the reference's zgemm3m) on/off.
+// The driver enables it for n >= 1024, where its 25 % saving matters and the solver's residual is about
+// half the reference's; below that the conventional four-product kernel keeps the last digit.
+void zgemm_allow_3m(int on);
 // same, restricted to the 64-column blocks cb0, cb0+cbs, cb0+2*cbs, ... (ncb of them) of C
 void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
                      size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,

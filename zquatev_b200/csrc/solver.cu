@@ -414,6 +414,7 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   w.A = Dfull;
   w.lda = ld;
   p->launches = 0;
+  zgemm_allow_3m(n >= 1024);
   cudaMemsetAsync(p->info_dev, 0, sizeof(int), st);
   cudaEventRecord(p->ev[1], st);
   if (dist) {

@@ -24,6 +24,8 @@ namespace zq {
 namespace {
 
 
+int g_allow_3m = 1;   // set per solve by the driver: small problems use the conventional product
+
 ZQ_D void cp_async16(void* smem, const void* gmem, bool pred) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   const int sz = pred ? 16 : 0;
@@ -329,7 +331,7 @@ void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const 
   static const int cfg_env = [] { const char* e = getenv("ZQ_GEMM_CFG"); return e ? atoi(e) : 0; }();
   // ZQ_GEMM_3M: 1 (default) = three-multiplication complex product (k_zgemm_3m), 0 = conventional four
   static const int use_3m = [] { const char* e = getenv("ZQ_GEMM_3M"); return e ? atoi(e) : 1; }();
-  if (use_3m && cfg_env == 0) {
+  if (use_3m && g_allow_3m && cfg_env == 0) {
     launch_3m<TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
     return;
   }
@@ -347,6 +349,8 @@ void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const 
 }
 
 }  // namespace
+
+void zgemm_allow_3m(int on) { g_allow_3m = on; }
 
 void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
                      size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
