@@ -75,6 +75,11 @@ int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt
 int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig,
                          long long strideEig, int* info);
 
+/* Counters of the batched entry since the library was loaded: problems replayed from a captured CUDA
+ * graph (one cudaGraphLaunch each) and problems enqueued kernel by kernel (the first use of every lane,
+ * ZQ_BATCH_GRAPH=0, or a failed capture).  Either pointer may be NULL.                              */
+void zquatev_b200_batched_stats(int* graph_launches, int* eager_solves);
+
 /* Multi-GPU (one process per GPU, NCCL over NVLink).  Rank 0 creates a 128-byte NCCL
  * unique id, the caller ships it to the other ranks (e.g. torch.distributed.broadcast), then every
  * rank calls dist_init on its own CUDA device.  libnccl.so.2 is loaded lazily by these calls.   */

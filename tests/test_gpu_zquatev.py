@@ -161,6 +161,32 @@ def test_values_only_and_bitwise_reproducible():
     assert info == 0 and np.max(np.abs(ev[:n] - e0[:n])) <= 1e-12 * np.abs(e0[:n]).max()
 
 
+def test_eigenvector_column_block():
+    """col0/ncols: the back-transformation of one eigenvector column block (what a rank of the multi-GPU solve
+    does) must give the same columns -- and their Kramers partners -- as the full solve.  n = 700 also
+    makes the split-K chunks of Y = Phi(V)^H X ragged (m not a multiple of the chunk length)."""
+    import torch
+    import zquatev_b200 as z
+    n, c0, nc = 700, 130, 190
+    M = O.gen_sym(n, 21)
+    buf0 = torch.from_numpy(np.asfortranarray(M).T.copy()).cuda()
+    eig = torch.zeros(n, dtype=torch.float64, device="cuda")
+    full = buf0.clone()
+    assert z.zquatev_device(2 * n, full.data_ptr(), 2 * n, eig.data_ptr()) == 0
+    e_full = eig.cpu().numpy().copy()
+    part = buf0.clone()
+    assert z.zquatev_device(2 * n, part.data_ptr(), 2 * n, eig.data_ptr(), col0=c0, ncols=nc) == 0
+    assert np.array_equal(e_full, eig.cpu().numpy())
+    F, P = full.cpu().numpy().T, part.cpu().numpy().T             # (row, col)
+    cols = np.r_[c0:c0 + nc, n + c0:n + c0 + nc]
+    # different split-K chunking (ncols enters the chunk count) -> equal to rounding, not bitwise
+    assert np.max(np.abs(F[:, cols] - P[:, cols])) <= 1e-12
+    U, V = P[:n, c0:c0 + nc], P[n:, c0:c0 + nc]
+    assert np.array_equal(P[:n, n + c0:n + c0 + nc], -V.conj()) and np.array_equal(P[n:, n + c0:n + c0 + nc], U.conj())
+    R = M @ P[:, c0:c0 + nc] - P[:, c0:c0 + nc] * e_full[c0:c0 + nc][None, :]
+    assert np.linalg.norm(R) <= 1e-13 * np.linalg.norm(M) * np.sqrt(nc) * 50
+
+
 def test_batched():
     import zquatev_b200 as z
     n, batch = 20, 5
@@ -174,6 +200,34 @@ def test_batched():
         assert np.max(np.abs(eig[b] - wr)) <= 1e-12 * np.abs(wr).max()
         out = D[b].T
         assert O.quality(Ms[b], out, eig[b])[2] == 0.0
+
+
+def test_batched_graph_replay():
+    """More problems than lanes: the first use of a lane is eager, the second captures the solve into a CUDA
+    graph, later ones replay it.  Every problem is different, so a replay that re-used stale operands would fail."""
+    import os
+    import zquatev_b200 as z
+    n, batch = 33, 56                                  # 16 lanes -> up to 4 problems per lane; n-1 not a panel multiple
+    Ms = [O.gen_sym(n, 2000 + b) for b in range(batch)]
+    D = np.stack([np.asfortranarray(M).T.copy() for M in Ms])
+    eig = np.zeros((batch, n))
+    g0, e0 = z.batched_stats()
+    info = z.zquatev_batched(D, eig)
+    g1, e1 = z.batched_stats()
+    assert np.all(info == 0)
+    assert (g1 - g0) + (e1 - e0) == batch
+    if os.environ.get("ZQ_BATCH_GRAPH", "1") != "0" and not os.environ.get("ZQ_BATCH_LANES"):
+        assert g1 - g0 == batch - 16, (g1 - g0, e1 - e0)   # everything after the first round of the 16 lanes is a replay
+    for b in range(batch):
+        wr = np.linalg.eigvalsh(Ms[b])[0::2]
+        assert np.max(np.abs(eig[b] - wr)) <= 1e-12 * np.abs(wr).max(), b
+        res, orth, pair = O.quality(Ms[b], D[b].T, eig[b])
+        assert pair == 0.0 and res < 1.0 and orth < 3.0, (b, res, orth)
+    # a second call with the same size re-uses lanes and graphs: all replays
+    D2 = np.stack([np.asfortranarray(M).T.copy() for M in Ms])
+    eig2 = np.zeros((batch, n))
+    info = z.zquatev_batched(D2, eig2)
+    assert np.all(info == 0) and np.array_equal(eig2, eig) and np.array_equal(D2, D)
 
 
 @pytest.mark.parametrize("n", [1024, 2048])

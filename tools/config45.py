@@ -74,4 +74,4 @@ else:
     dloop = (time.time() - t0) / min(batch, 32)
     print(json.dumps({"config": 5, "batch": batch, "n2": 2 * n, "all_info_zero": ok, "seconds_first_call": dt0, "seconds": dt,
                       "ms_per_matrix": dt / batch * 1e3, "ms_per_matrix_single_entry_loop": dloop * 1e3, "max_eig_dev_rel": worst,
-                      "max_res_orth_pair": wq, "gflops_canonical": 164.0 / 3.0 * n ** 3 * batch / dt * 1e-9}), flush=True)
+                      "max_res_orth_pair": wq, "graph_launches_eager_solves": z.batched_stats(), "gflops_canonical": 164.0 / 3.0 * n ** 3 * batch / dt * 1e-9}), flush=True)

@@ -13,6 +13,7 @@ no CPU path: importing works anywhere, calling without the library or a CUDA dev
 from .api import (  # noqa: F401
     LIB_PATH,
     ZqOptions,
+    batched_stats,
     last_phases,
     lib,
     release,
@@ -23,5 +24,5 @@ from .api import (  # noqa: F401
     zquatev_device,
 )
 
-__all__ = ["zquatev", "zquatev_device", "zquatev_batched", "last_phases", "set_profiling", "release", "version",
+__all__ = ["zquatev", "zquatev_device", "zquatev_batched", "batched_stats", "last_phases", "set_profiling", "release", "version",
            "lib", "LIB_PATH", "ZqOptions"]

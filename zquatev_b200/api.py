@@ -24,6 +24,7 @@ SYMBOLS = {
     "zquatev_b200": (_I, [_I, _P, _I, _P]),
     "zquatev_b200_ex": (_I, [_I, _P, _I, _P, ctypes.POINTER(ZqOptions)]),
     "zquatev_b200_batched": (_I, [_I, _I, _P, _I, _LL, _P, _LL, _P]),
+    "zquatev_b200_batched_stats": (None, [_P, _P]),
     "zquatev_b200_release": (None, []),
     "zquatev_b200_dist_unique_id": (_I, [_P]),
     "zquatev_b200_dist_init": (_I, [_I, _I, _P]),
@@ -102,6 +103,13 @@ def zquatev_batched(D: np.ndarray, eig: np.ndarray) -> np.ndarray:
     rc = lib().zquatev_b200_batched(batch, n2, D.ctypes.data, n2, n2 * n2, eig.ctypes.data, eig.shape[-1], info.ctypes.data)
     _check(rc if rc < 0 else 0, "zquatev_batched")
     return info
+
+
+def batched_stats():
+    """(graph_launches, eager_solves) of zquatev_batched since the library was loaded."""
+    g, e = ctypes.c_int(0), ctypes.c_int(0)
+    lib().zquatev_b200_batched_stats(ctypes.byref(g), ctypes.byref(e))
+    return g.value, e.value
 
 
 def last_phases():

@@ -111,6 +111,20 @@ __global__ void __launch_bounds__(256) k_swap_pairing(int n, cplx* Out, size_t l
   R[n + r] = cconj(u);
 }
 
+// deterministic split-K reduction: Y = parts[0] + parts[1] + ... (fixed order)
+__global__ void __launch_bounds__(256) k_sum_parts(size_t count, int nparts, const cplx* __restrict__ parts, size_t stride,
+                                                   cplx* __restrict__ Y) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (size_t)gridDim.x * 256) {
+    cplx acc = parts[i];
+    for (int z = 1; z < nparts; ++z) {
+      const cplx t = parts[(size_t)z * stride + i];
+      acc.x += t.x;
+      acc.y += t.y;
+    }
+    Y[i] = acc;
+  }
+}
+
 __global__ void k_check_finite(int n, const double* d, const double* e, int* flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -138,6 +152,13 @@ void launch_scale_Z(int n, int ncols, const double* Z, size_t ldz, const int* pe
   if (ncols <= 0) return;
   dim3 g((n + 255) / 256, ncols);
   k_scale_Z<<<g, 256, 0, st>>>(n, Z, ldz, perm, s, X, ldx);
+}
+
+void launch_sum_parts(size_t count, int nparts, const cplx* parts, size_t stride, cplx* Y, cudaStream_t st) {
+  if (count == 0 || nparts <= 0) return;
+  size_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_sum_parts<<<(unsigned)blocks, 256, 0, st>>>(count, nparts, parts, stride, Y);
 }
 
 void launch_pairing(int n, cplx* Out, size_t ld, cudaStream_t st) {

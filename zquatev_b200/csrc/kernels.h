@@ -87,6 +87,15 @@ void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStr
 void launch_zgemm(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
                   size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
                   size_t sC, cudaStream_t st);
+// split-K form (alpha = 1, beta = 0): the K range is cut into `nseg` segments (operand offsets segA, segB elements
+// apart; K = length of one segment) of `chunks` pieces of kc each; piece z = seg*chunks + c writes its own partial
+// product to Cparts + z*sC.  The caller sums the parts in a fixed order (launch_sum_parts): deterministic, no atomics.
+// Used for Y = Phi(V)^H X of the back-transformation, whose 128 x ncols output gives too few CTAs on its own.
+struct SplitK { int chunks = 0, kc = 0; size_t segA = 0, segB = 0; };
+void launch_zgemm_splitk(int ta, int tb, int M, int N, int K, const cplx* A, size_t lda, const cplx* B, size_t ldb,
+                         cplx* Cparts, size_t ldc, size_t sC, int nseg, const SplitK& sk, cudaStream_t st);
+// Y[i] = sum_z parts[z*stride + i], i < count (complex), z ascending
+void launch_sum_parts(size_t count, int nparts, const cplx* parts, size_t stride, cplx* Y, cudaStream_t st);
 // 3M complex product (three real DMMA products per complex product, as the reference's zgemm3m) on/off.
 // The driver enables it for n >= 1024, where its 25 % saving matters and the solver's residual is about
 // half the reference's; below that the conventional four-product kernel keeps the last digit.

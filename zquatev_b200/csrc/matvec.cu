@@ -87,7 +87,7 @@ ZQ_D void tile_body(const cplx* __restrict__ A, size_t lda, int n, int r0, int c
 
 __global__ void __launch_bounds__(256, 2)
 k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __restrict__ vq, quat* __restrict__ pd,
-         quat* __restrict__ pt, int nI, int jfirst, int jstride,
+         quat* __restrict__ pt, int nI, int jfirst, int jstride, int nJ, int rev,
          // fused panel dots
          const cplx* __restrict__ pan, int nb, int ncols, quat* __restrict__ dotW, quat* __restrict__ dotV) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -119,8 +119,11 @@ k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __res
   __shared__ quat vcol[TC];
   __shared__ quat red[NW][TR];
   TileIdx ti;
-  ti.I = s / TR + blockIdx.x;
-  ti.J = jfirst + blockIdx.y * jstride;                 // owned column blocks only (multi-GPU)
+  // rev: sweep the tile grid backwards.  Consecutive columns alternate the direction, so the ~100 MB of D and E that
+  // the previous sweep touched last are still in the 126 MB L2 when this one starts there (and the first sweep after
+  // a trailing update starts where the GEMM wrote last).  Tile -> partial-buffer mapping is unchanged: same sums.
+  ti.I = s / TR + (rev ? nI - 1 - (int)blockIdx.x : (int)blockIdx.x);
+  ti.J = jfirst + (rev ? nJ - 1 - (int)blockIdx.y : (int)blockIdx.y) * jstride;   // owned column blocks only (multi-GPU)
   if (2 * ti.I + 1 < ti.J || ti.J * TC >= n) return;    // tile entirely above the diagonal / no owned block
   const int r0 = ti.I * TR, c0 = ti.J * TC;
   if (threadIdx.x < TC) {
@@ -179,14 +182,16 @@ void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int ncols = k - j0;
   const int nch = ncols > 0 ? (n - s + DOT_ROWS - 1) / DOT_ROWS : 0;
   if (nJ == 0 && nch == 0) return;
-  k_matvec<<<dim3(nI + nch, nJ > 0 ? nJ : 1), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, jfirst, w.world, w.pan,
-                                                           w.nb, ncols, w.dotW, w.dotV);
+  static const int zigzag = [] { const char* e = getenv("ZQ_K1_ZIGZAG"); return e ? atoi(e) : 1; }();
+  const int rev = (zigzag && nJ > 0 && ((k - j0) & 1) == 0) ? 1 : 0;
+  k_matvec<<<dim3(nI + nch, nJ > 0 ? nJ : 1), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, jfirst, w.world, nJ > 0 ? nJ : 1,
+                                                           rev, w.pan, w.nb, ncols, w.dotW, w.dotV);
 }
 
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st) {
   const int n = w.n;
   const int nI = (n - 1) / TR - s / TR + 1, nJ = (n - 1) / TC - s / TC + 1;
-  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, s / TC, 1, w.pan, w.nb, 0, w.dotW, w.dotV);
+  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, s / TC, 1, nJ, 0, w.pan, w.nb, 0, w.dotW, w.dotV);
   k_matvec_gather<<<(n - s + 255) / 256, 256, 0, st>>>(n, s, w.pd, w.pt, y);
 }
 

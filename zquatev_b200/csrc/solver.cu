@@ -28,12 +28,15 @@ namespace zq {
 
 constexpr int DEFAULT_NB = 64;
 constexpr int MAX_NB = 64;
+constexpr int YP_PARTS = 8;        // split-K workspace of the back-transformation: 8 partial Y at ncols = n
+constexpr int YP_MAX_CHUNKS = 8;   // at most 8 K-chunks per (a-rows / b-rows) segment
 
 struct Plan {
   int n = 0, nb = 0, device = -1;
   char* slab = nullptr;
   PanelWs pw{};
-  cplx *L = nullptr, *R = nullptr, *P = nullptr, *T = nullptr, *Y = nullptr, *TY = nullptr;
+  cplx *L = nullptr, *R = nullptr, *P = nullptr, *T = nullptr, *Y = nullptr, *TY = nullptr, *YP = nullptr;
+  size_t yp_elems = 0;       // capacity of YP (split-K partial products of Y = Phi(V)^H X)
   quat* s = nullptr;
   double* bis = nullptr;
   int* info_dev = nullptr;
@@ -44,6 +47,7 @@ struct Plan {
   std::vector<cudaEvent_t> k1ev;
   double phase_ms[8] = {};
   long launches = 0;
+  bool timing = true;        // false while a solve is being captured into a CUDA graph (no event records)
 };
 
 // ---- NCCL, resolved at run time (no link dependency: single-GPU users never load it) ----------
@@ -126,6 +130,8 @@ static int plan_create(int n, int nb, Plan** out) {
   const size_t o_L = take(2 * N * 4 * nb * sizeof(cplx)), o_R = take(N * 4 * nb * sizeof(cplx));
   const size_t o_P = take(2 * N * 2 * nb * sizeof(cplx)), o_T = take((size_t)4 * nb * nb * sizeof(cplx));
   const size_t o_Y = take((size_t)2 * nb * N * sizeof(cplx)), o_TY = take((size_t)2 * nb * N * sizeof(cplx));
+  p->yp_elems = (size_t)YP_PARTS * 2 * nb * N;
+  const size_t o_YP = take(p->yp_elems * sizeof(cplx));
   const size_t o_s = take(N * sizeof(quat)), o_bis = take((N + 8) * 8), o_info = take(256), o_eig = take(N * 8);
   cudaError_t e = cudaMalloc(&p->slab, bytes);
   if (e != cudaSuccess) { delete p; return zq_cuda_fail(e, __FILE__, __LINE__); }
@@ -138,7 +144,7 @@ static int plan_create(int n, int nb, Plan** out) {
   w.d = (double*)(b + o_d); w.e = (double*)(b + o_e); w.tau = (double*)(b + o_tau); w.alpha = (quat*)(b + o_al);
   w.G = (quat*)(b + o_G);
   p->L = (cplx*)(b + o_L); p->R = (cplx*)(b + o_R); p->P = (cplx*)(b + o_P); p->T = (cplx*)(b + o_T);
-  p->Y = (cplx*)(b + o_Y); p->TY = (cplx*)(b + o_TY); p->s = (quat*)(b + o_s); p->bis = (double*)(b + o_bis);
+  p->Y = (cplx*)(b + o_Y); p->TY = (cplx*)(b + o_TY); p->YP = (cplx*)(b + o_YP); p->s = (quat*)(b + o_s); p->bis = (double*)(b + o_bis);
   p->info_dev = (int*)(b + o_info); p->eig_dev = (double*)(b + o_eig);
   for (auto& ev : p->ev) cudaEventCreate(&ev);
   *out = p;
@@ -201,7 +207,7 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
   if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
-  const bool prof = g_profile;
+  const bool prof = g_profile && p->timing;
   if (prof && p->k1ev.size() < 2 * (size_t)n) {
     const size_t old = p->k1ev.size();
     p->k1ev.resize(2 * (size_t)n);
@@ -394,9 +400,30 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
     const size_t ldp = 2 * (size_t)m;
     cplx* Xa = X + (size_t)(j0 + 1);
     cplx* Xb = X + (size_t)(n + j0 + 1);
-    // Y = P^H X   (two K segments: a-rows and b-rows)
-    launch_zgemm(1, 0, 2 * kb, ncols, m, cmake(1, 0), p->P, ldp, Xa, ldx, cmake(0, 0), p->Y, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
-    launch_zgemm(1, 0, 2 * kb, ncols, m, cmake(1, 0), p->P + m, ldp, Xb, ldx, cmake(1, 0), p->Y, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
+    // Y = P^H X.  K runs over two segments (a-rows, b-rows of P and X); its 2kb x ncols output alone gives
+    // 2 x ncols/32 CTAs (1024 at ncols = 16384: 2.3 waves; 128 on an 8-GPU column shard: under one wave), so the
+    // segments are cut into K-chunks that run as one launch and are summed in a fixed order.
+    static const int splitk = [] { const char* e = getenv("ZQ_BT_SPLITK"); return e ? atoi(e) : 1; }();
+    if (!splitk) {   // development knob: the two-launch form (a-rows, then b-rows accumulated on top)
+      launch_zgemm(1, 0, 2 * kb, ncols, m, cmake(1, 0), p->P, ldp, Xa, ldx, cmake(0, 0), p->Y, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
+      launch_zgemm(1, 0, 2 * kb, ncols, m, cmake(1, 0), p->P + m, ldp, Xb, ldx, cmake(1, 0), p->Y, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
+    } else {
+      const size_t ypart = (size_t)2 * kb * ncols;
+      const int ctas1 = ((2 * kb + 63) / 64) * 2 * ((ncols + 63) / 64);
+      int chunks = (8 * 444 + 2 * ctas1 - 1) / (2 * ctas1);            // aim at >= 8 waves of 3 CTAs x 148 SMs
+      const int cap_mem = (int)(p->yp_elems / ypart / 2), cap_k = m / 256;
+      if (chunks > cap_mem) chunks = cap_mem;
+      if (chunks > YP_MAX_CHUNKS) chunks = YP_MAX_CHUNKS;
+      if (chunks > cap_k) chunks = cap_k;
+      if (chunks < 1) chunks = 1;
+      SplitK sk;
+      sk.kc = (((m + chunks - 1) / chunks) + 7) & ~7;
+      sk.chunks = (m + sk.kc - 1) / sk.kc;
+      sk.segA = (size_t)m;                     // b-rows of P
+      sk.segB = (size_t)n;                     // b-rows of X
+      launch_zgemm_splitk(1, 0, 2 * kb, ncols, m, p->P, ldp, Xa, ldx, p->YP, 2 * (size_t)kb, ypart, 2, sk, st);
+      launch_sum_parts(ypart, 2 * sk.chunks, p->YP, ypart, p->Y, st);
+    }
     // TY = T Y
     launch_zgemm(0, 0, 2 * kb, ncols, 2 * kb, cmake(1, 0), p->T, 2 * (size_t)kb, p->Y, 2 * (size_t)kb, cmake(0, 0), p->TY,
                  2 * (size_t)kb, 0, 1, 0, 0, 0, st);
@@ -416,7 +443,7 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   p->launches = 0;
   zgemm_allow_3m(n >= 1024);
   cudaMemsetAsync(p->info_dev, 0, sizeof(int), st);
-  cudaEventRecord(p->ev[1], st);
+  if (p->timing) cudaEventRecord(p->ev[1], st);
   if (dist) {
     if (!g_comm) return -6;
     const int rc = tridiagonalise_dist(p, st);
@@ -425,11 +452,11 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     tridiagonalise(p, st);
   }
   launch_check_finite(n, w.d, w.e, p->info_dev, st);
-  cudaEventRecord(p->ev[2], st);
+  if (p->timing) cudaEventRecord(p->ev[2], st);
   if (!jobz) {
     launch_bisect(n, w.d, w.e, eig_dev, p->bis, st);
-    cudaEventRecord(p->ev[3], st);
-    cudaEventRecord(p->ev[4], st);
+    if (p->timing) cudaEventRecord(p->ev[3], st);
+    if (p->timing) cudaEventRecord(p->ev[4], st);
   } else {
     if (!p->dc) {
       p->dc = dc_create(n);
@@ -444,7 +471,7 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     int rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st, dist ? &dd : nullptr);
     if (rc) return rc;
     p->launches += dc_launches(p->dc) + 3;
-    cudaEventRecord(p->ev[3], st);
+    if (p->timing) cudaEventRecord(p->ev[3], st);
     cplx* X = Dfull + (size_t)n * ld;          // right half is scratch until the pairing
     launch_phase_chain(n, w.alpha, w.e, p->s, st);
     if (dist) {                                 // eigenvector columns split evenly over the ranks
@@ -476,7 +503,7 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
         ZQ_NCCL_CHECK(g_nccl.GroupEnd());
       }
     }
-    cudaEventRecord(p->ev[4], st);
+    if (p->timing) cudaEventRecord(p->ev[4], st);
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return zq_cuda_fail(e, __FILE__, __LINE__);
@@ -578,6 +605,71 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
 
 using namespace zq;
 
+// Batched small problems (BASELINE config 5): the problems are independent, so they are pipelined
+// over LANES concurrent CUDA streams, each with its own plan (workspace) and pinned staging -- the
+// latency-bound kernels of different problems share the GPU.  A solve of 2n = 512 is ~1200 dependent
+// launches of a few microseconds each, so the host's launch rate is the limit when it enqueues them one
+// by one; every lane therefore CAPTURES its solve (H2D, all kernels, D2H) once into a CUDA graph and
+// replays it for the following problems: one cudaGraphLaunch per problem.  ZQ_BATCH_GRAPH=0 keeps the
+// eager path (also taken if capture or instantiation fails).  (The reference has no batched entry: its
+// callers loop over zquatev().)
+namespace {
+struct Lane {
+  Plan* p = nullptr;
+  cudaStream_t st = nullptr;
+  int* hinfo = nullptr;
+  cplx* hbuf = nullptr;
+  double* heig = nullptr;
+  cudaGraphExec_t gexec = nullptr;
+  int uses = 0;
+  bool graph_failed = false;
+};
+std::vector<Lane> g_lanes;
+int g_lanes_n = -1;
+int g_batch_graph_launches = 0, g_batch_eager_solves = 0;
+
+void lanes_free() {
+  for (auto& L : g_lanes) {
+    if (L.st) cudaStreamSynchronize(L.st);
+    if (L.gexec) cudaGraphExecDestroy(L.gexec);
+    if (L.p) plan_free(L.p);
+    if (L.st) cudaStreamDestroy(L.st);
+    if (L.hinfo) cudaFreeHost(L.hinfo);
+    if (L.hbuf) cudaFreeHost(L.hbuf);
+    if (L.heig) cudaFreeHost(L.heig);
+  }
+  g_lanes.clear();
+  g_lanes_n = -1;
+}
+
+// H2D of the left half, full solve, D2H of the result / eigenvalues / status: everything a lane does for one problem
+int lane_enqueue(Lane& L, int n) {
+  const int n2 = 2 * n;
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(L.p->Dfull, L.hbuf, (size_t)n * n2 * sizeof(cplx), cudaMemcpyHostToDevice, L.st));
+  const int rc = solve_device(L.p, L.p->Dfull, (size_t)n2, L.p->eig_dev, 1, 0, 0, 0, 0, L.st);
+  if (rc) return rc;
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(L.hbuf, L.p->Dfull, (size_t)n2 * n2 * sizeof(cplx), cudaMemcpyDeviceToHost, L.st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(L.heig, L.p->eig_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, L.st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(L.hinfo, L.p->info_dev, sizeof(int), cudaMemcpyDeviceToHost, L.st));
+  return 0;
+}
+
+// capture one solve of this lane into an executable graph; false = keep the eager path
+bool lane_capture(Lane& L, int n) {
+  if (cudaStreamBeginCapture(L.st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return false; }
+  L.p->timing = false;
+  const int rc = lane_enqueue(L, n);
+  L.p->timing = true;
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(L.st, &g);
+  bool ok = (rc == 0 && e == cudaSuccess && g != nullptr);
+  if (ok && cudaGraphInstantiate(&L.gexec, g, 0) != cudaSuccess) { L.gexec = nullptr; ok = false; }
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();
+  return ok;
+}
+}  // namespace
+
 extern "C" {
 
 int zquatev_b200(int n2, void* D, int ld2, double* eig) { return solve_any(n2, D, ld2, eig, nullptr); }
@@ -586,10 +678,7 @@ int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt
   return solve_any(n2, D, ld2, eig, opt);
 }
 
-// Batched small problems (BASELINE config 5): the problems are independent, so they are pipelined
-// over LANES concurrent CUDA streams, each with its own plan (workspace) -- H2D of problem b+LANES
-// overlaps the kernels of problems b+1.., and the latency-bound kernels of different problems share
-// the GPU.  (The reference has no batched entry: its callers loop over zquatev().)
+// Batched entry: see the lane machinery above.
 int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig, long long strideEig,
                          int* info) {
   if (batch < 0) return -1;
@@ -598,15 +687,16 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
   if (rc) return rc;
   if (n2 == 0) return 0;
   const int n = n2 / 2;
-  constexpr int LANES = 8;
+  static const int use_graph = [] { const char* e = getenv("ZQ_BATCH_GRAPH"); return e ? atoi(e) : 1; }();
+  static const int lanes_env = [] { const char* e = getenv("ZQ_BATCH_LANES"); return e ? atoi(e) : 0; }();
+  const int LANES = lanes_env > 0 ? (lanes_env < 64 ? lanes_env : 64) : (use_graph ? 16 : 8);
   std::lock_guard<std::mutex> lk(g_mu);
-  struct Lane { Plan* p = nullptr; cudaStream_t st = nullptr; int* hinfo = nullptr; cplx* hbuf = nullptr; double* heig = nullptr; };
-  static std::vector<Lane> lanes;
-  static int lanes_n = -1;
+  std::vector<Lane>& lanes = g_lanes;
   const int nl = batch < LANES ? batch : LANES;
-  if (lanes_n != n || (int)lanes.size() < nl) {
-    for (auto& L : lanes) { if (L.p) { cudaStreamSynchronize(L.st); plan_free(L.p); } if (L.st) cudaStreamDestroy(L.st); if (L.hinfo) cudaFreeHost(L.hinfo); if (L.hbuf) cudaFreeHost(L.hbuf); if (L.heig) cudaFreeHost(L.heig); }
+  if (g_lanes_n != n || (int)lanes.size() < nl) {
+    lanes_free();
     lanes.assign(nl, Lane());
+    g_lanes_n = n;
     for (auto& L : lanes) {
       rc = plan_create(n, DEFAULT_NB, &L.p);
       if (rc) return rc;
@@ -617,11 +707,10 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
       ZQ_CUDA_CHECK(cudaMallocHost(&L.hbuf, (size_t)n2 * n2 * sizeof(cplx)));
       ZQ_CUDA_CHECK(cudaMallocHost(&L.heig, (size_t)n * sizeof(double)));
     }
-    lanes_n = n;
   }
   const size_t ld = (size_t)n2;
   int worst = 0;
-  std::vector<int> pending(nl, -1);            // problem whose info sits in the lane's pinned word
+  std::vector<int> pending(nl, -1);            // problem whose result sits in the lane's pinned staging
   auto harvest = [&](int l) {
     if (pending[l] < 0) return 0;
     cudaError_t e = cudaStreamSynchronize(lanes[l].st);
@@ -645,12 +734,18 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
     if (rc) return rc;
     cplx* Db = (cplx*)D + (size_t)b * strideD;
     for (int c = 0; c < n; ++c) memcpy(L.hbuf + (size_t)c * n2, Db + (size_t)c * ld2, (size_t)n2 * sizeof(cplx));
-    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.p->Dfull, L.hbuf, (size_t)n * n2 * sizeof(cplx), cudaMemcpyHostToDevice, L.st));
-    rc = solve_device(L.p, L.p->Dfull, ld, L.p->eig_dev, 1, 0, 0, 0, 0, L.st);
-    if (rc) return rc;
-    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.hbuf, L.p->Dfull, (size_t)n2 * n2 * sizeof(cplx), cudaMemcpyDeviceToHost, L.st));
-    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.heig, L.p->eig_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, L.st));
-    ZQ_CUDA_CHECK(cudaMemcpyAsync(L.hinfo, L.p->info_dev, sizeof(int), cudaMemcpyDeviceToHost, L.st));
+    // the first problem of a lane runs eagerly (it also creates the D&C workspace and sets the kernel attributes,
+    // which must not happen inside a capture); the second use captures, later ones replay
+    if (use_graph && !L.gexec && !L.graph_failed && L.uses >= 1) L.graph_failed = !lane_capture(L, n);
+    if (L.gexec) {
+      ZQ_CUDA_CHECK(cudaGraphLaunch(L.gexec, L.st));
+      ++g_batch_graph_launches;
+    } else {
+      rc = lane_enqueue(L, n);
+      if (rc) return rc;
+      ++g_batch_eager_solves;
+    }
+    ++L.uses;
     pending[l] = b;
   }
   for (int l = 0; l < nl; ++l) {
@@ -658,6 +753,12 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
     if (rc) return rc;
   }
   return worst;
+}
+
+void zquatev_b200_batched_stats(int* graph_launches, int* eager_solves) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (graph_launches) *graph_launches = g_batch_graph_launches;
+  if (eager_solves) *eager_solves = g_batch_eager_solves;
 }
 
 int zquatev_b200_dist_unique_id(void* id128) {
@@ -697,6 +798,7 @@ void zquatev_b200_dist_finalize(void) {
 void zquatev_b200_release(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_plan) { cudaDeviceSynchronize(); plan_free(g_plan); g_plan = nullptr; }
+  lanes_free();
 }
 
 int zquatev_b200_last_phases(double ms[8]) {

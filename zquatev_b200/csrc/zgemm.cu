@@ -72,7 +72,8 @@ struct OpTile {
 template <int BM, int BN, int BK, int STAGES, int TA, int TB>
 __global__ void __launch_bounds__((BM / 32) * (BN / 32) * 32)
 k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t lda, const cplx* __restrict__ B,
-            size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC, int cb0, int cbs) {
+            size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC, int cb0, int cbs,
+            SplitK sk) {
   constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
   using TileA = OpTile<BM, TA == 1, BK>;
   using TileB = OpTile<BN, TB == 0, BK>;
@@ -82,8 +83,16 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
 
   const int r0 = blockIdx.x * BM, c0 = (cb0 + blockIdx.y * cbs) * BN;
   if (lower && r0 + BM - 1 < c0) return;
-  A += (size_t)blockIdx.z * sA;
-  B += (size_t)blockIdx.z * sB;
+  if (sk.chunks > 0) {
+    // split-K: grid.z = segments x chunks; part z covers k in [c*kc, c*kc + kc) of segment seg and owns its own C
+    const int seg = blockIdx.z / sk.chunks, k0 = (blockIdx.z % sk.chunks) * sk.kc;
+    A += (size_t)seg * sk.segA + (TA ? (size_t)k0 : (size_t)k0 * lda);
+    B += (size_t)seg * sk.segB + (TB ? (size_t)k0 * ldb : (size_t)k0);
+    K = min(sk.kc, K - k0);
+  } else {
+    A += (size_t)blockIdx.z * sA;
+    B += (size_t)blockIdx.z * sB;
+  }
   C += (size_t)blockIdx.z * sC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp % (BM / 32)) * 32, wn = (warp / (BM / 32)) * 32;
@@ -188,7 +197,8 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
 template <int BK, int STAGES, int TA, int TB>
 __global__ void __launch_bounds__(128)
 k_zgemm_3m(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t lda, const cplx* __restrict__ B,
-           size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC, int cb0, int cbs) {
+           size_t ldb, cplx beta, cplx* __restrict__ C, size_t ldc, int lower, size_t sA, size_t sB, size_t sC, int cb0, int cbs,
+           SplitK sk) {
   constexpr int BM = 64, BN = 32, NTHREADS = 128;
   using TileA = OpTile<BM, TA == 1, BK>;
   using TileB = OpTile<BN, TB == 0, BK>;
@@ -199,8 +209,16 @@ k_zgemm_3m(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t l
   const int r0 = blockIdx.x * BM;
   const int c0 = (cb0 + (blockIdx.y >> 1) * cbs) * 64 + (blockIdx.y & 1) * BN;
   if (c0 >= N || (lower && r0 + BM - 1 < c0)) return;
-  A += (size_t)blockIdx.z * sA;
-  B += (size_t)blockIdx.z * sB;
+  if (sk.chunks > 0) {
+    // split-K: grid.z = segments x chunks; part z covers k in [c*kc, c*kc + kc) of segment seg and owns its own C
+    const int seg = blockIdx.z / sk.chunks, k0 = (blockIdx.z % sk.chunks) * sk.kc;
+    A += (size_t)seg * sk.segA + (TA ? (size_t)k0 : (size_t)k0 * lda);
+    B += (size_t)seg * sk.segB + (TB ? (size_t)k0 * ldb : (size_t)k0);
+    K = min(sk.kc, K - k0);
+  } else {
+    A += (size_t)blockIdx.z * sA;
+    B += (size_t)blockIdx.z * sB;
+  }
   C += (size_t)blockIdx.z * sC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
@@ -292,7 +310,8 @@ k_zgemm_3m(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t l
 
 template <int TA, int TB>
 void launch_3m(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
-               size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
+               size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, SplitK sk,
+               cudaStream_t st) {
   constexpr int BK = 8, STAGES = 3;
   using TileA = OpTile<64, TA == 1, BK>;
   using TileB = OpTile<32, TB == 0, BK>;
@@ -304,12 +323,13 @@ void launch_3m(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const
   }
   dim3 g((M + 63) / 64, ncb >= 0 ? 2 * ncb : 2 * ((N + 63) / 64), batch);
   if (g.y == 0) return;
-  k_zgemm_3m<BK, STAGES, TA, TB><<<g, 128, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC, cb0, cbs);
+  k_zgemm_3m<BK, STAGES, TA, TB><<<g, 128, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC, cb0, cbs, sk);
 }
 
 template <int BM, int BN, int BK, int STAGES, int TA, int TB>
 void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
-                size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
+                size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, SplitK sk,
+                cudaStream_t st) {
   using TileA = OpTile<BM, TA == 1, BK>;
   using TileB = OpTile<BN, TB == 0, BK>;
   constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
@@ -321,18 +341,19 @@ void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, cons
   }
   dim3 g((M + BM - 1) / BM, ncb >= 0 ? ncb : (N + BN - 1) / BN, batch);
   if (g.y == 0) return;
-  k_zgemm_mma<BM, BN, BK, STAGES, TA, TB><<<g, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC, cb0, cbs);
+  k_zgemm_mma<BM, BN, BK, STAGES, TA, TB><<<g, NTHREADS, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC, cb0, cbs, sk);
 }
 
 template <int TA, int TB>
 void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
-              size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
+              size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, SplitK sk,
+              cudaStream_t st) {
   // ZQ_GEMM_CFG (development knob): 0 auto, 1: 64x128 BK16 x3, 2: 64x64 BK16 x2 (2 CTAs/SM), 3: 64x64 BK8 x3
   static const int cfg_env = [] { const char* e = getenv("ZQ_GEMM_CFG"); return e ? atoi(e) : 0; }();
   // ZQ_GEMM_3M: 1 (default) = three-multiplication complex product (k_zgemm_3m), 0 = conventional four
   static const int use_3m = [] { const char* e = getenv("ZQ_GEMM_3M"); return e ? atoi(e) : 1; }();
   if (use_3m && g_allow_3m && cfg_env == 0) {
-    launch_3m<TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+    launch_3m<TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
     return;
   }
   int cfg = cfg_env;
@@ -341,11 +362,11 @@ void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const 
     cfg = 3;   // measured best on every shape of the solver (profiles/r01_gemm_configs.md)
   }
   if (cfg == 1)
-    launch_cfg<64, 128, 16, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+    launch_cfg<64, 128, 16, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
   else if (cfg == 2)
-    launch_cfg<64, 64, 16, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+    launch_cfg<64, 64, 16, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
   else
-    launch_cfg<64, 64, 8, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+    launch_cfg<64, 64, 8, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
 }
 
 }  // namespace
@@ -356,10 +377,22 @@ void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx
                      size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
                      size_t sC, int cb0, int cbs, int ncb, cudaStream_t st) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
-  if (ta == 0 && tb == 0) launch_t<0, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
-  else if (ta == 0 && tb == 1) launch_t<0, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
-  else if (ta == 1 && tb == 0) launch_t<1, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
-  else launch_t<1, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, st);
+  const SplitK sk{};
+  if (ta == 0 && tb == 0) launch_t<0, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
+  else if (ta == 0 && tb == 1) launch_t<0, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
+  else if (ta == 1 && tb == 0) launch_t<1, 0>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
+  else launch_t<1, 1>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
+}
+
+void launch_zgemm_splitk(int ta, int tb, int M, int N, int K, const cplx* A, size_t lda, const cplx* B, size_t ldb,
+                         cplx* Cparts, size_t ldc, size_t sC, int nseg, const SplitK& sk, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || nseg <= 0 || sk.chunks <= 0) return;
+  const int batch = nseg * sk.chunks;
+  const cplx one = cmake(1, 0), zero = cmake(0, 0);
+  if (ta == 0 && tb == 0) launch_t<0, 0>(M, N, K, one, A, lda, B, ldb, zero, Cparts, ldc, 0, batch, 0, 0, sC, 0, 1, -1, sk, st);
+  else if (ta == 0 && tb == 1) launch_t<0, 1>(M, N, K, one, A, lda, B, ldb, zero, Cparts, ldc, 0, batch, 0, 0, sC, 0, 1, -1, sk, st);
+  else if (ta == 1 && tb == 0) launch_t<1, 0>(M, N, K, one, A, lda, B, ldb, zero, Cparts, ldc, 0, batch, 0, 0, sC, 0, 1, -1, sk, st);
+  else launch_t<1, 1>(M, N, K, one, A, lda, B, ldb, zero, Cparts, ldc, 0, batch, 0, 0, sC, 0, 1, -1, sk, st);
 }
 
 void launch_zgemm(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
