@@ -64,6 +64,56 @@ struct OpTile {
   static ZQ_D cplx frag(const cplx* sm, int t, int k) { return sm[KCONT ? t * LD + k : k * LD + t]; }
 };
 
+// Per-thread cp.async schedule of one operand tile.  Of a thread's (t, k) elements one index is the same for
+// every element and the other advances by a constant, so everything except the k-tail test is computed once
+// before the main loop: a stage costs one predicate, one 64-bit add and one LDGSTS per 16 bytes (the generic
+// index arithmetic of OpTile::load was ~25 integer instructions per copy, issued in front of every DMMA block).
+template <int BT, bool KCONT, int BK, int NT>
+struct TileLoader {
+  using Tile = OpTile<BT, KCONT, BK>;
+  static constexpr int PER = (BT * BK) / NT;                  // 16-byte copies per thread per stage
+  static constexpr int ISTEP = KCONT ? NT / BK : NT / BT;     // distance of consecutive copies in the varying index
+  static_assert((BT * BK) % NT == 0 && (KCONT ? NT % BK == 0 : NT % BT == 0), "tile / thread count mismatch");
+  const cplx* p0;      // source of copy 0 of the next stage
+  const cplx* safe;    // any valid address (zero-fill copies read nothing)
+  size_t istride;      // elements between consecutive copies
+  size_t kstep;        // elements between consecutive stages
+  int s0;              // shared-memory element offset of copy 0
+  int kfix;            // k of copy 0 inside the stage
+  unsigned okmask;     // bit i: copy i is inside the tile dimension
+  ZQ_D void init(const cplx* G, size_t ldg, int t0, int Tmax, int tid) {
+    safe = G;
+    istride = (size_t)ISTEP * ldg;
+    if (KCONT) {
+      const int k = tid % BK, tb = tid / BK;
+      p0 = G + (size_t)k + (size_t)(t0 + tb) * ldg;
+      kstep = BK;
+      s0 = tb * Tile::LD + k;
+      kfix = k;
+      okmask = 0;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) okmask |= (t0 + tb + i * ISTEP < Tmax) ? (1u << i) : 0u;
+    } else {
+      const int t = tid % BT, kb = tid / BT;
+      p0 = G + (size_t)(t0 + t) + (size_t)kb * ldg;
+      kstep = (size_t)BK * ldg;
+      s0 = kb * Tile::LD + t;
+      kfix = kb;
+      okmask = (t0 + t < Tmax) ? 0xffffffffu : 0u;
+    }
+  }
+  // stage whose first k is k0 (stages must be issued in order: p0 advances)
+  ZQ_D void issue(cplx* sm, int k0, int K) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int k = KCONT ? kfix : kfix + i * ISTEP;
+      const bool ok = ((okmask >> i) & 1u) && (k0 + k < K);
+      cp_async16(sm + s0 + i * (ISTEP * Tile::LD), ok ? p0 + (size_t)i * istride : safe, ok);
+    }
+    p0 += kstep;
+  }
+};
+
 // TA/TB: 0 = operand used as stored, 1 = conjugate transpose.
 //   A as stored (TA=0) is M x K (contiguous along m)  -> KCONT = false
 //   A^H       (TA=1) is stored K x M (contiguous along k) -> KCONT = true, conj
@@ -114,12 +164,15 @@ k_zgemm_mma(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t 
     for (int j = 0; j < 4; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
 
   const int nk = (K + BK - 1) / BK;
+  TileLoader<BM, TA == 1, BK, NTHREADS> ldA;
+  TileLoader<BN, TB == 0, BK, NTHREADS> ldB;
+  ldA.init(A, lda, r0, M, tid);
+  ldB.init(B, ldb, c0, N, tid);
   auto issue = [&](int kt) {
     if (kt < nk) {
       cplx* sa = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
-      cplx* sb = sa + TileA::ELEMS;
-      TileA::template load<NTHREADS>(sa, A, lda, r0, kt * BK, M, K, tid);
-      TileB::template load<NTHREADS>(sb, B, ldb, c0, kt * BK, N, K, tid);
+      ldA.issue(sa, kt * BK, K);
+      ldB.issue(sa + TileA::ELEMS, kt * BK, K);
     }
     cp_async_commit();
   };
@@ -241,12 +294,15 @@ k_zgemm_3m(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t l
       for (int h = 0; h < 2; ++h) t1[i][j][h] = t2[i][j][h] = t3[i][j][h] = 0.0;
 
   const int nk = (K + BK - 1) / BK;
+  TileLoader<BM, TA == 1, BK, NTHREADS> ldA;
+  TileLoader<BN, TB == 0, BK, NTHREADS> ldB;
+  ldA.init(A, lda, r0, M, tid);
+  ldB.init(B, ldb, c0, N, tid);
   auto issue = [&](int kt) {
     if (kt < nk) {
       cplx* sa = smem + (size_t)(kt % STAGES) * STAGE_ELEMS;
-      cplx* sb = sa + TileA::ELEMS;
-      TileA::template load<NTHREADS>(sa, A, lda, r0, kt * BK, M, K, tid);
-      TileB::template load<NTHREADS>(sb, B, ldb, c0, kt * BK, N, K, tid);
+      ldA.issue(sa, kt * BK, K);
+      ldB.issue(sa + TileA::ELEMS, kt * BK, K);
     }
     cp_async_commit();
   };
