@@ -254,6 +254,7 @@ def main():
     step_device()
     torch.cuda.synchronize()
     ph = z.last_phases()
+    k4_ms = z.last_trailing_ms() if world == 1 else 0.0
     z.set_profiling(False)
     barrier()
     if rank == 0:
@@ -347,6 +348,24 @@ def main():
                                   "peak_source": "own measurement (profiles/r01_fp64_peak.jsonl: DMMA 37.1, DFMA 36.9 TFLOP/s); MEASURED_PEAKS.json has no FP64 entry",
                                   "note": "phase time includes operand staging, T factors, pairing and (N > 1) the NCCL gather"},
                 "cpu_baseline": cpu, "e2e": e2e}
+        if world == 1 and k4_ms > 0:
+            # third roofline: the trailing rank-2k update [D;E] -= L R^H (K4), event pair around each of its n/nb launches in
+            # the profiled step.  canonical flops = 32 m^2 kb per panel (lower triangles of D and E, K = 4 kb complex)
+            nbb = args.nb or 64
+            f4 = 0.0
+            for j0 in range(0, n - 1, nbb):
+                kb = min(nbb, n - 1 - j0)
+                m = n - (j0 + kb)
+                if m > 0:
+                    f4 += 32.0 * m * m * kb
+            ex = GEMM_EXEC if n >= 1024 else 1.0
+            line["roofline_fp64_trailing"] = {
+                "kernel": "k_zgemm_3m<0,1> lower (K4 trailing rank-2k update, DMMA m8n8k4)", "bound": "tensor",
+                "achieved": ex * f4 / (k4_ms * 1e-3) * 1e-12, "peak": 37.1, "unit": "TFLOP/s",
+                "frac": ex * f4 / (k4_ms * 1e-3) * 1e-12 / 37.1, "canonical_tflops": f4 / (k4_ms * 1e-3) * 1e-12,
+                "k4_ms_per_step": k4_ms, "share_of_step": k4_ms / ph["device_total"] if ph["device_total"] else None,
+                "launches": (n - 1 + nbb - 1) // nbb,
+                "peak_source": "own measurement (profiles/r01_fp64_peak.jsonl)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         from zquatev_b200 import dist as zd

@@ -102,6 +102,9 @@ void zquatev_b200_release(void);
 int zquatev_b200_last_phases(double ms[8]);
 /* 1: also time every K1 launch with its own event pair (slower; for bench.py roofline).        */
 void zquatev_b200_set_profiling(int on);
+/* Milliseconds spent in the trailing-update GEMMs (K4) of the last PROFILED single-GPU solve (event pair
+ * around each of the n/nb launches); 0 when profiling was off.                                         */
+double zquatev_b200_last_trailing_ms(void);
 
 /* Library build info, e.g. "zquatev_b200 0.1 sm_100a nb=32".                                   */
 const char* zquatev_b200_version(void);

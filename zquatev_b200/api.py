@@ -32,6 +32,7 @@ SYMBOLS = {
     "zquatev_b200_dist_transport": (_I, []),
     "zquatev_b200_last_phases": (_I, [_P]),
     "zquatev_b200_set_profiling": (None, [_I]),
+    "zquatev_b200_last_trailing_ms": (_D, []),
     "zquatev_b200_version": (ctypes.c_char_p, []),
     "zq_test_matvec": (_I, [_I, _I, _P, _LL, _P, _P, _I, _P]),
     "zq_test_zgemm": (_I, [_I, _I, _I, _I, _I, _P, _P, _LL, _P, _LL, _P, _P, _LL, _I, _I, _P]),
@@ -119,6 +120,11 @@ def last_phases():
         return None
     keys = ["h2d", "tridiag", "tridiag_eig", "backtransform", "d2h", "device_total", "k1_matvec", "launches"]
     return dict(zip(keys, list(ms)))
+
+
+def last_trailing_ms() -> float:
+    """device milliseconds of the trailing-update GEMMs of the last profiled single-GPU solve"""
+    return float(lib().zquatev_b200_last_trailing_ms())
 
 
 def set_profiling(on: bool):

@@ -45,6 +45,8 @@ struct Plan {
   double* eig_dev = nullptr;
   cudaEvent_t ev[6] = {};
   std::vector<cudaEvent_t> k1ev;
+  std::vector<cudaEvent_t> k4ev;   // profiling: event pair around every trailing-update GEMM
+  double k4_ms = 0;
   double phase_ms[8] = {};
   long launches = 0;
   bool timing = true;        // false while a solve is being captured into a CUDA graph (no event records)
@@ -103,6 +105,7 @@ static void plan_free(Plan* p) {
   if (p->dc) dc_destroy(p->dc);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   for (auto& e : p->k1ev) cudaEventDestroy(e);
+  for (auto& e : p->k4ev) cudaEventDestroy(e);
   delete p;
 }
 
@@ -213,6 +216,11 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
     p->k1ev.resize(2 * (size_t)n);
     for (size_t i = old; i < p->k1ev.size(); ++i) cudaEventCreate(&p->k1ev[i]);
   }
+  if (prof && p->k4ev.size() < 2 * (size_t)(n / nb + 1)) {
+    const size_t old = p->k4ev.size();
+    p->k4ev.resize(2 * (size_t)(n / nb + 1));
+    for (size_t i = old; i < p->k4ev.size(); ++i) cudaEventCreate(&p->k4ev[i]);
+  }
   for (int j0 = 0; j0 < n - 1; j0 += nb) {
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
     for (int i = 0; i < kb; ++i) {
@@ -229,9 +237,11 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
     const int r0 = j0 + kb, m = n - r0;
     if (m > 0) {
       launch_build_LR(w, r0, kb, p->L, p->R, st);
+      if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
       // [D;E][r0:, r0:] -= L R^H on the lower triangles: batch 0 = D block, batch 1 = E block
       launch_zgemm(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
                    w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, st);
+      if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb) + 1], st);
       p->launches += 3;
     }
   }
@@ -525,6 +535,16 @@ static void collect_phases(Plan* p, bool host_mode) {
     for (int k = 0; k + 1 < p->n; ++k)
       if (cudaEventElapsedTime(&t, p->k1ev[2 * k], p->k1ev[2 * k + 1]) == cudaSuccess) tot += t;
     ms[6] = tot;
+    // trailing-update GEMMs (single-GPU path): panels [0, n-1) step nb, the last one has no trailing matrix
+    double t4 = 0;
+    const int nb = p->nb, n = p->n;
+    for (int j0 = 0; j0 < n - 1; j0 += nb) {
+      const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
+      if (n - (j0 + kb) <= 0 || 2 * (size_t)(j0 / nb) + 1 >= p->k4ev.size()) continue;
+      if (cudaEventElapsedTime(&t, p->k4ev[2 * (j0 / nb)], p->k4ev[2 * (j0 / nb) + 1]) == cudaSuccess) t4 += t;
+    }
+    cudaGetLastError();
+    p->k4_ms = t4;
   }
   ms[7] = (double)p->launches;
 }
@@ -809,6 +829,11 @@ int zquatev_b200_last_phases(double ms[8]) {
 }
 
 void zquatev_b200_set_profiling(int on) { g_profile = on != 0; }
+
+double zquatev_b200_last_trailing_ms(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_plan ? g_plan->k4_ms : 0.0;
+}
 
 const char* zquatev_b200_version(void) { return "zquatev_b200 0.1 sm_100a nb=64"; }
 
