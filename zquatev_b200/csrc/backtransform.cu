@@ -34,7 +34,15 @@ __global__ void __launch_bounds__(256) k_build_phi(PanelWs w, int j0, int kb, cp
 // T = Phi(T_q), T_q upper triangular quaternion kb x kb:
 //   T_q[i,i] = tau_i ;  T_q[0:i, i] = -tau_i T_q[0:i,0:i] g_i ,  g_i = V[:, 0:i]^H v_i  (saved in G)
 // so that H_{j0} ... H_{j0+kb-1} = I - V T_q V^H (forward, column-wise; zlarft analogue).
-__global__ void __launch_bounds__(128) k_build_T(PanelWs w, int j0, int kb, cplx* T) {
+// One CTA per panel (blockIdx.x = panel index, its T at T + blockIdx.x * 4 nb^2): the column recurrence is serial
+// inside a panel (64 dependent steps, ~180 us), but G and tau of ALL panels are known once the reduction is done,
+// so every T is built by one launch before the back-transformation instead of one launch per panel on its
+// critical path (11 ms of 80 ms at n = 4096).
+__global__ void __launch_bounds__(128) k_build_T(PanelWs w, cplx* Tall) {
+  const int j0 = blockIdx.x * w.nb;
+  const int kb = min(w.nb, w.n - 1 - j0);
+  if (kb <= 0) return;
+  cplx* T = Tall + (size_t)blockIdx.x * 4 * w.nb * w.nb;
   const int ld = 2 * kb, t = threadIdx.x;
   for (int idx = t; idx < ld * ld; idx += blockDim.x) T[idx] = cmake(0, 0);
   __syncthreads();
@@ -60,16 +68,37 @@ __global__ void __launch_bounds__(128) k_build_T(PanelWs w, int j0, int kb, cplx
 }
 
 // s_0 = 1, s_{k+1} = (alpha_k/|alpha_k|) s_k : diag(s)^H T_q diag(s) is real symmetric.
-__global__ void k_phase_chain(int n, const quat* alpha, const double* e, quat* s) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  quat cur = qmake(cmake(1, 0), cmake(0, 0));
-  s[0] = cur;
-  for (int k = 0; k + 1 < n; ++k) {
-    const double ek = e[k];
-    if (ek > 0.0) {
-      cur = qmul(qscale(alpha[k], 1.0 / ek), cur);
-      cur = qscale(cur, rsqrt(qnorm2(cur)));
-    }
+// Ordered prefix product of unit quaternions (associative, not commutative) as a one-CTA scan: thread t owns a
+// contiguous segment of len links, forms the segment product, the segment products are scanned across the CTA
+// (Hillis-Steele in shared memory, later factor on the LEFT), then every thread replays its segment on top of
+// the product of all earlier segments.  Each s_k is renormalised, so rounding cannot drift off the unit sphere.
+constexpr int PC_NT = 1024;
+ZQ_D quat pc_link(const quat* alpha, const double* e, int k) {
+  const double ek = e[k];
+  return ek > 0.0 ? qscale(alpha[k], 1.0 / ek) : qmake(cmake(1, 0), cmake(0, 0));
+}
+ZQ_D quat pc_unit(quat q) { return qscale(q, rsqrt(qnorm2(q))); }
+__global__ void __launch_bounds__(PC_NT) k_phase_chain(int n, const quat* __restrict__ alpha, const double* __restrict__ e,
+                                                       quat* __restrict__ s) {
+  __shared__ quat sc[PC_NT];
+  const int t = threadIdx.x, links = n - 1;
+  const int len = (links + PC_NT - 1) / PC_NT;
+  const int k0 = t * len, k1 = min(links, k0 + len);
+  quat seg = qmake(cmake(1, 0), cmake(0, 0));
+  for (int k = k0; k < k1; ++k) seg = pc_unit(qmul(pc_link(alpha, e, k), seg));
+  sc[t] = seg;
+  __syncthreads();
+  for (int off = 1; off < PC_NT; off <<= 1) {
+    quat mine = sc[t];
+    if (t >= off) mine = pc_unit(qmul(mine, sc[t - off]));
+    __syncthreads();
+    sc[t] = mine;
+    __syncthreads();
+  }
+  quat cur = t > 0 ? sc[t - 1] : qmake(cmake(1, 0), cmake(0, 0));   // product of all earlier segments = s[k0]
+  if (t == 0) s[0] = cur;
+  for (int k = k0; k < k1; ++k) {
+    cur = pc_unit(qmul(pc_link(alpha, e, k), cur));
     s[k + 1] = cur;
   }
 }
@@ -139,12 +168,13 @@ void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st
   k_build_phi<<<g, 256, 0, st>>>(w, j0, kb, P);
 }
 
-void launch_build_T(const PanelWs& w, int j0, int kb, cplx* T, cudaStream_t st) {
-  k_build_T<<<1, 128, 0, st>>>(w, j0, kb, T);
+void launch_build_T_all(const PanelWs& w, cplx* Tall, cudaStream_t st) {
+  const int npanels = (w.n - 1 + w.nb - 1) / w.nb;
+  if (npanels > 0) k_build_T<<<npanels, 128, 0, st>>>(w, Tall);
 }
 
 void launch_phase_chain(int n, const quat* alpha, const double* e, quat* s, cudaStream_t st) {
-  k_phase_chain<<<1, 32, 0, st>>>(n, alpha, e, s);
+  k_phase_chain<<<1, PC_NT, 0, st>>>(n, alpha, e, s);
 }
 
 void launch_scale_Z(int n, int ncols, const double* Z, size_t ldz, const int* perm, const quat* s, cplx* X, size_t ldx,

@@ -84,6 +84,17 @@ ZQ_D double warp_sum(double v) {
 ZQ_D cplx warp_sum(cplx v) { v.x = warp_sum(v.x); v.y = warp_sum(v.y); return v; }
 ZQ_D quat warp_sum(quat v) { v.a = warp_sum(v.a); v.b = warp_sum(v.b); return v; }
 
+// Programmatic dependent launch (PDL): the per-column kernels of the reduction are short and strictly dependent, so
+// their launch latency is on the critical path n times.  Each chain kernel starts with pdl_enter(): it lets the NEXT
+// kernel of the stream be scheduled as soon as every CTA of this one is resident (its CTAs then sit in
+// griddepcontrol.wait) and itself waits until the PREVIOUS grid has completed and its writes are visible -- so
+// nothing that reads or writes global memory may precede it.  Both instructions are no-ops in a launch without the
+// programmatic-serialization attribute (launch_chain, kernels.h).
+ZQ_D void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // streaming 16-byte load that does not allocate in L1 (matrix data is touched once per pass)
 ZQ_D cplx ld_stream(const cplx* p) {
   cplx v;

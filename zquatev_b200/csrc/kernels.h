@@ -8,10 +8,37 @@ namespace zq {
 // ---- geometry of the K1 tiles (shared by matvec.cu and panel.cu) ----
 constexpr int MV_TR = 128;   // tile rows  (4 rows per lane)
 constexpr int MV_TC = 64;    // tile cols  (8 warps x 8 columns)
-constexpr int DOT_ROWS = 512;
+// panel inner products (W^H v, V^H v) fused into the K1 launch: rows [s, n) are cut into at most DOT_MAX_CHUNKS
+// chunks of dot_chunk_rows(n - s) rows and the panel columns into groups of 8 (one warp per column), one CTA per
+// (chunk, group) -- a short column still spreads over many SMs (a fixed 512-row chunk left ONE CTA with the whole
+// panel at m = 512: K1 took 13 us at panel column 0 and 49 us at column 60).
+constexpr int DOT_MIN_ROWS = 128, DOT_MAX_CHUNKS = 32;
+__host__ __device__ inline int dot_chunk_rows(int rows) {
+  int r = DOT_MIN_ROWS;
+  while ((rows + r - 1) / r > DOT_MAX_CHUNKS) r *= 2;
+  return r;
+}
 constexpr int ROWS_PER_CTA = 256;
 constexpr int PANEL_ROWS = 32;      // rows per CTA of the latency-bound panel kernels
 constexpr int MAX_NB_PANEL = 64;    // largest panel width
+
+// launch of a kernel of the per-column chain: with ZQ_PDL != 0 (default) the launch carries the programmatic-stream-
+// serialization attribute, see pdl_enter() in common.cuh
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 struct PanelWs {
   int n, nb;
@@ -108,8 +135,8 @@ void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx
 // K6 helpers (backtransform.cu)
 //   P = Phi(V) of panel [j0, j0+kb): (2m x 2kb), ld 2m, m = n-1-j0 ; rows [0,m) <-> a-part rows j0+1..
 void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st);
-//   T (2kb x 2kb complex, ld 2kb) from saved Gram columns G and tau
-void launch_build_T(const PanelWs& w, int j0, int kb, cplx* T, cudaStream_t st);
+//   T of every panel (panel j at Tall + j * 4 nb^2: 2kb x 2kb complex, ld 2kb) from saved Gram columns G and tau
+void launch_build_T_all(const PanelWs& w, cplx* Tall, cudaStream_t st);
 //   phase chain s (n quats) from alpha; X0 = diag(s) Z[:, perm]
 void launch_phase_chain(int n, const quat* alpha, const double* e, quat* s, cudaStream_t st);
 void launch_scale_Z(int n, int ncols, const double* Z, size_t ldz, const int* perm, const quat* s, cplx* X, size_t ldx,

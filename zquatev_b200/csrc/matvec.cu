@@ -15,7 +15,8 @@
 // a fixed order -> bit-reproducible, no atomics.
 //
 // The same launch carries extra CTAs that compute the partial panel inner products
-// W^H v and V^H v (skinny GEMV^H over rows [s, n)), which the correction step needs.
+// W^H v and V^H v (skinny GEMV^H over rows [s, n)), which the correction step needs: one CTA per
+// (row chunk, group of 8 panel columns), see dot_chunk_rows (kernels.h).
 #include "kernels.h"
 
 namespace zq {
@@ -89,30 +90,32 @@ __global__ void __launch_bounds__(256, 2)
 k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __restrict__ vq, quat* __restrict__ pd,
          quat* __restrict__ pt, int nI, int jfirst, int jstride, int nJ, int rev,
          // fused panel dots
-         const cplx* __restrict__ pan, int nb, int ncols, quat* __restrict__ dotW, quat* __restrict__ dotV) {
+         const cplx* __restrict__ pan, int nb, int ncols, int nch, int crows, quat* __restrict__ dotW, quat* __restrict__ dotV) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_enter();
   if ((int)blockIdx.x >= nI) {
-    // ---- panel inner products: chunk of DOT_ROWS rows, warp per column t (only in grid row y = 0) ----
-    if (blockIdx.y != 0) return;
-    const int ch = blockIdx.x - nI;
-    const int ra = s + ch * DOT_ROWS, rb = min(n, ra + DOT_ROWS);
-    for (int t = warp; t < ncols; t += NW) {
-      const cplx* va = pan + ((size_t)(0 * nb + t)) * n;
-      const cplx* vb = pan + ((size_t)(1 * nb + t)) * n;
-      const cplx* wa = pan + ((size_t)(2 * nb + t)) * n;
-      const cplx* wb = pan + ((size_t)(3 * nb + t)) * n;
-      quat aW = qzero(), aV = qzero();
-      for (int r = ra + lane; r < rb; r += 32) {
-        const quat f = vq[r];
-        qfma_cj(aW, qmake(wa[r], wb[r]), f);
-        qfma_cj(aV, qmake(va[r], vb[r]), f);
-      }
-      aW = warp_sum(aW);
-      aV = warp_sum(aV);
-      if (lane == 0) {
-        dotW[(size_t)ch * nb + t] = aW;
-        dotV[(size_t)ch * nb + t] = aV;
-      }
+    // ---- panel inner products: the grid cells right of the tile columns, flattened, one per (row chunk, group of
+    // 8 panel columns); warp = one panel column, lanes stride the chunk's rows ----
+    const int id = ((int)blockIdx.x - nI) + ((int)gridDim.x - nI) * (int)blockIdx.y;
+    const int ch = id % nch, t = (id / nch) * NW + warp;
+    if (t >= ncols) return;
+    const int ra = s + ch * crows, rb = min(n, ra + crows);
+    const cplx* va = pan + ((size_t)(0 * nb + t)) * n;
+    const cplx* vb = pan + ((size_t)(1 * nb + t)) * n;
+    const cplx* wa = pan + ((size_t)(2 * nb + t)) * n;
+    const cplx* wb = pan + ((size_t)(3 * nb + t)) * n;
+    quat aW = qzero(), aV = qzero();
+#pragma unroll 4
+    for (int r = ra + lane; r < rb; r += 32) {
+      const quat f = vq[r];
+      qfma_cj(aW, qmake(wa[r], wb[r]), f);
+      qfma_cj(aV, qmake(va[r], vb[r]), f);
+    }
+    aW = warp_sum(aW);
+    aV = warp_sum(aV);
+    if (lane == 0) {
+      dotW[(size_t)ch * nb + t] = aW;
+      dotV[(size_t)ch * nb + t] = aV;
     }
     return;
   }
@@ -180,18 +183,21 @@ void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
   int jfirst, nJ;
   owned_blocks(w, s, jfirst, nJ);
   const int ncols = k - j0;
-  const int nch = ncols > 0 ? (n - s + DOT_ROWS - 1) / DOT_ROWS : 0;
-  if (nJ == 0 && nch == 0) return;
+  const int crows = dot_chunk_rows(n - s);
+  const int nch = ncols > 0 ? (n - s + crows - 1) / crows : 0;
+  const int ndot = nch * ((ncols + NW - 1) / NW);       // (row chunk, group of 8 panel columns) cells
+  if (nJ == 0 && ndot == 0) return;
   static const int zigzag = [] { const char* e = getenv("ZQ_K1_ZIGZAG"); return e ? atoi(e) : 1; }();
   const int rev = (zigzag && nJ > 0 && ((k - j0) & 1) == 0) ? 1 : 0;
-  k_matvec<<<dim3(nI + nch, nJ > 0 ? nJ : 1), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, jfirst, w.world, nJ > 0 ? nJ : 1,
-                                                           rev, w.pan, w.nb, ncols, w.dotW, w.dotV);
+  const int gy = nJ > 0 ? nJ : 1;
+  launch_chain(k_matvec, dim3(nI + (ndot + gy - 1) / gy, gy), dim3(256), st, w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, jfirst, w.world, gy,
+               rev, w.pan, w.nb, ncols, nch > 0 ? nch : 1, crows, w.dotW, w.dotV);
 }
 
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st) {
   const int n = w.n;
   const int nI = (n - 1) / TR - s / TR + 1, nJ = (n - 1) / TC - s / TC + 1;
-  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, s / TC, 1, nJ, 0, w.pan, w.nb, 0, w.dotW, w.dotV);
+  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, s / TC, 1, nJ, 0, w.pan, w.nb, 0, 1, DOT_MIN_ROWS, w.dotW, w.dotV);
   k_matvec_gather<<<(n - s + 255) / 256, 256, 0, st>>>(n, s, w.pd, w.pt, y);
 }
 

@@ -85,6 +85,7 @@ ZQ_D void px_signal(const PeerX& px, unsigned int* counter, int flag_index, unsi
 // col_update: rows r in [k, n)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int ng_parts) {
+  pdl_enter();
   const int n = w.n, i = k - j0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = k + blockIdx.x * PR + lane;
@@ -128,7 +129,10 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
   __syncthreads();
 
   quat part = qzero();     // - sum over this warp's panel columns
+  quat acol = qzero();     // A(r, k): issued before the panel loop so its HBM latency hides behind it
+  if (warp == 0 && act) acol = qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]);
   if (act) {
+#pragma unroll 4
     for (int t = warp; t < i; t += NW) {
       quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
       quat wrt = (t == i - 1) ? wr : qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
   quat col = warps_sum(part, red, warp, lane);
   double nr = 0.0;
   if (warp == 0 && act) {
-    col = qadd(col, qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]));
+    col = qadd(col, acol);
     if (r == k) {
       w.d[k] = col.a.x;
     } else {
@@ -158,6 +162,7 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
 // ---------------------------------------------------------------------------------------------
 template <bool PX>
 __global__ void __launch_bounds__(NT) k_reflector(PanelWs w, PeerX px, int k, int j0, int nparts, unsigned long long seq) {
+  pdl_enter();
   const int n = w.n, i = k - j0;
   const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
   __shared__ double s_red[32];
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(NT) k_reflector(PanelWs w, PeerX px, int k, in
 // multi-GPU: vq[k+1 .. n+2) has just been broadcast from the owner of column k
 template <bool PX>
 __global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, PeerX px, int k, int j0, unsigned long long seq) {
+  pdl_enter();
   const int n = w.n, i = k - j0;
   const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
   const quat* src = PX ? px.bvq[px.rank] : w.vq;
@@ -251,6 +257,7 @@ __global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, PeerX px, int k, int
 // staging buffer and signals; 4 waits for all slots and sums them in rank order.
 template <int MODE>
 __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int k, int j0, int nch, unsigned long long seq) {
+  pdl_enter();
   constexpr bool PART = (MODE == 1 || MODE == 3), FIN = (MODE == 2 || MODE == 4);
   const int n = w.n, i = k - j0, s = k + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -265,6 +272,7 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int 
       const int tt = t >> 1;
       const quat* src = (t & 1) ? w.dotV : w.dotW;
       quat acc = qzero();
+#pragma unroll 8
       for (int c = 0; c < nch; ++c) acc = qadd(acc, src[(size_t)c * w.nb + tt]);
       if (t & 1) gV[tt] = acc; else gW[tt] = acc;
     }
@@ -282,9 +290,12 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int 
       const int Ilo = max(I0, (r / MV_TC) / 2);
       // owned column blocks only: J = jfirst, jfirst + world, ...  (world == 1: all)
       const int jfirst = J0 + ((w.rank - J0 % w.world) + w.world) % w.world;
+#pragma unroll 4
       for (int J = jfirst + warp * w.world; J <= Jhi; J += NW * w.world) part = qadd(part, w.pd[(size_t)J * n + r]);
-      if ((r / MV_TC) % w.world == w.rank)     // transposed sums exist only on the owner of r's column block
+      if ((r / MV_TC) % w.world == w.rank) {   // transposed sums exist only on the owner of r's column block
+#pragma unroll 4
         for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
+      }
     } else if (warp == 0) {
       if (MODE == 2) {
         part = w.p[r];                         // all-reduced M v (NCCL)
@@ -294,6 +305,7 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int 
       }
     }
     if (!PART) {
+#pragma unroll 4
       for (int t = warp; t < i; t += NW) {
         quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
         quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
@@ -331,6 +343,7 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int 
 
 // finish w of the LAST column of a panel (col_update does it for the others)
 __global__ void __launch_bounds__(NT) k_finish_w(PanelWs w, int k, int j0, int ng_parts) {
+  pdl_enter();
   const int n = w.n, i = k - j0;
   const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
   __shared__ double s_red[32];
@@ -376,60 +389,60 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k;                    // rows k..n-1
   const int ng = (k > j0) ? cdiv(w.n - k, PR) : 0;   // g_part written by reduce_correct of column k-1 (rows k..n-1)
-  k_col_update<<<cdiv(rows, PR), NT, 0, st>>>(w, k, j0, ng);
+  launch_chain(k_col_update, dim3(cdiv(rows, PR)), dim3(NT), st, w, k, j0, ng);
 }
 
 void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nparts = cdiv(w.n - k, PR);        // nrm_part written by col_update (rows k..n-1)
-  k_reflector<false><<<cdiv(rows, NT), NT, 0, st>>>(w, PeerX{}, k, j0, nparts, 0ull);
+  launch_chain(k_reflector<false>, dim3(cdiv(rows, NT)), dim3(NT), st, w, PeerX{}, k, j0, nparts, 0ull);
 }
 
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  const int nch = cdiv(rows, DOT_ROWS);
-  k_reduce_correct<0><<<cdiv(rows, PR), NT, 0, st>>>(w, PeerX{}, k, j0, nch, 0ull);
+  const int nch = cdiv(rows, dot_chunk_rows(rows));
+  launch_chain(k_reduce_correct<0>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, 0ull);
 }
 
 void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_reduce_correct<1><<<cdiv(rows, PR), NT, 0, st>>>(w, PeerX{}, k, k, 0, 0ull);
+  launch_chain(k_reduce_correct<1>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, k, 0, 0ull);
 }
 
 void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  const int nch = cdiv(rows, DOT_ROWS);
-  k_reduce_correct<2><<<cdiv(rows, PR), NT, 0, st>>>(w, PeerX{}, k, j0, nch, 0ull);
+  const int nch = cdiv(rows, dot_chunk_rows(rows));
+  launch_chain(k_reduce_correct<2>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, 0ull);
 }
 
 void launch_unpack_v(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_unpack_v<false><<<cdiv(rows, NT), NT, 0, st>>>(w, PeerX{}, k, j0, 0ull);
+  launch_chain(k_unpack_v<false>, dim3(cdiv(rows, NT)), dim3(NT), st, w, PeerX{}, k, j0, 0ull);
 }
 
 void launch_reflector_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_reflector<true><<<cdiv(rows, NT), NT, 0, st>>>(w, px, k, j0, cdiv(w.n - k, PR), seq);
+  launch_chain(k_reflector<true>, dim3(cdiv(rows, NT)), dim3(NT), st, w, px, k, j0, cdiv(w.n - k, PR), seq);
 }
 
 void launch_wait_unpack_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_unpack_v<true><<<cdiv(rows, NT), NT, 0, st>>>(w, px, k, j0, seq);
+  launch_chain(k_unpack_v<true>, dim3(cdiv(rows, NT)), dim3(NT), st, w, px, k, j0, seq);
 }
 
 void launch_reduce_partial_px(const PanelWs& w, const PeerX& px, int k, unsigned long long seq, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_reduce_correct<3><<<cdiv(rows, PR), NT, 0, st>>>(w, px, k, k, 0, seq);
+  launch_chain(k_reduce_correct<3>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, k, 0, seq);
 }
 
 void launch_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_reduce_correct<4><<<cdiv(rows, PR), NT, 0, st>>>(w, px, k, j0, cdiv(rows, DOT_ROWS), seq);
+  launch_chain(k_reduce_correct<4>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, cdiv(rows, dot_chunk_rows(rows)), seq);
 }
 
 void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  k_finish_w<<<cdiv(rows, NT), NT, 0, st>>>(w, k, j0, cdiv(rows, PR));
+  launch_chain(k_finish_w, dim3(cdiv(rows, NT)), dim3(NT), st, w, k, j0, cdiv(rows, PR));
 }
 
 void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStream_t st) {

@@ -111,6 +111,11 @@ static void plan_free(Plan* p) {
 
 static int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("ZQ_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
+
 static int plan_create(int n, int nb, Plan** out) {
   Plan* p = new Plan();
   p->n = n;
@@ -124,14 +129,14 @@ static int plan_create(int n, int nb, Plan** out) {
   const size_t o_x = take(N * sizeof(quat)), o_vq = take((N + 2) * sizeof(quat)), o_p = take(N * sizeof(quat));
   const size_t o_pd = take((size_t)cdiv(n, MV_TC) * N * sizeof(quat));
   const size_t o_pt = take((size_t)cdiv(n, MV_TR) * N * sizeof(quat));
-  const size_t nch = (size_t)cdiv(n, DOT_ROWS) + 1;
+  const size_t nch = DOT_MAX_CHUNKS + 1;
   const size_t o_dW = take(nch * nb * sizeof(quat)), o_dV = take(nch * nb * sizeof(quat));
   const size_t nparts = (size_t)cdiv(n, PANEL_ROWS) + 1;
   const size_t o_np = take(nparts * 8), o_gp = take(nparts * 8);
   const size_t o_d = take(N * 8), o_e = take(N * 8), o_tau = take(N * 8), o_al = take(N * sizeof(quat));
   const size_t o_G = take(N * nb * sizeof(quat));
   const size_t o_L = take(2 * N * 4 * nb * sizeof(cplx)), o_R = take(N * 4 * nb * sizeof(cplx));
-  const size_t o_P = take(2 * N * 2 * nb * sizeof(cplx)), o_T = take((size_t)4 * nb * nb * sizeof(cplx));
+  const size_t o_P = take(2 * N * 2 * nb * sizeof(cplx)), o_T = take((size_t)cdiv(n, nb) * 4 * nb * nb * sizeof(cplx));   // T of every panel
   const size_t o_Y = take((size_t)2 * nb * N * sizeof(cplx)), o_TY = take((size_t)2 * nb * N * sizeof(cplx));
   p->yp_elems = (size_t)YP_PARTS * 2 * nb * N;
   const size_t o_YP = take(p->yp_elems * sizeof(cplx));
@@ -402,11 +407,12 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
   const int n = w.n, nb = w.nb;
   if (n < 2 || ncols <= 0) return;
   const int last = ((n - 2) / nb) * nb;
+  launch_build_T_all(w, p->T, st);
+  p->launches += 1;
   for (int j0 = last; j0 >= 0; j0 -= nb) {
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
     const int m = n - 1 - j0;
     launch_build_phi(w, j0, kb, p->P, st);
-    launch_build_T(w, j0, kb, p->T, st);
     const size_t ldp = 2 * (size_t)m;
     cplx* Xa = X + (size_t)(j0 + 1);
     cplx* Xb = X + (size_t)(n + j0 + 1);
@@ -435,12 +441,12 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
       launch_sum_parts(ypart, 2 * sk.chunks, p->YP, ypart, p->Y, st);
     }
     // TY = T Y
-    launch_zgemm(0, 0, 2 * kb, ncols, 2 * kb, cmake(1, 0), p->T, 2 * (size_t)kb, p->Y, 2 * (size_t)kb, cmake(0, 0), p->TY,
+    launch_zgemm(0, 0, 2 * kb, ncols, 2 * kb, cmake(1, 0), p->T + (size_t)(j0 / nb) * 4 * nb * nb, 2 * (size_t)kb, p->Y, 2 * (size_t)kb, cmake(0, 0), p->TY,
                  2 * (size_t)kb, 0, 1, 0, 0, 0, st);
     // X -= P TY   (batch 0: a-rows, batch 1: b-rows)
     launch_zgemm(0, 0, m, ncols, 2 * kb, cmake(-1, 0), p->P, ldp, p->TY, 2 * (size_t)kb, cmake(1, 0), Xa, ldx, 0, 2,
                  (size_t)m, 0, (size_t)n, st);
-    p->launches += 6;
+    p->launches += 5;
   }
 }
 
