@@ -156,6 +156,83 @@ def tridiagonalise(D, E, nb):
     return d, ala, alb, tau, D, E
 
 
+def tridiagonalise_one_cta(D, E, nb):
+    """K5 (small.cu) restated step by step: unblocked reduction of ONE small matrix in which the pass
+    that applies the rank-2 update of column k-1 (M -= v_{k-1} w_{k-1}^H + w_{k-1} v_{k-1}^H, lower
+    triangles) also forms y = M v_k from the updated entries.  Same reflector formulas as
+    `tridiagonalise`, so d / alpha / tau / reflector tails agree to rounding for every nb.
+    Additionally returns G[k, t] = V_t^H v_k (t < k - j0: earlier reflectors of the same panel),
+    the quantity the device keeps for the compact-WY T factors."""
+    D = D.copy()
+    E = E.copy()
+    n = D.shape[0]
+    d = np.zeros(n)
+    ala = np.zeros(max(n - 1, 0), dtype=np.complex128)
+    alb = np.zeros(max(n - 1, 0), dtype=np.complex128)
+    tau = np.zeros(max(n - 1, 0))
+    Ga = np.zeros((n, nb), dtype=np.complex128)
+    Gb = np.zeros((n, nb), dtype=np.complex128)
+    vpa = np.zeros(n, dtype=np.complex128)
+    vpb = np.zeros(n, dtype=np.complex128)
+    wa = np.zeros(n, dtype=np.complex128)
+    wb = np.zeros(n, dtype=np.complex128)
+
+    def rank2(ra, rb, cidx):
+        """(vp wv^H + wv vp^H)[rows, cidx] as a quaternion (a, b) column"""
+        q1 = qmul((vpa[ra:rb], vpb[ra:rb]), qconj((wa[cidx], wb[cidx])))
+        q2 = qmul((wa[ra:rb], wb[ra:rb]), qconj((vpa[cidx], vpb[cidx])))
+        return q1[0] + q2[0], q1[1] + q2[1]
+
+    for k in range(n - 1):
+        s = k + 1
+        j0 = (k // nb) * nb
+        i = k - j0
+        # (a) column k, fully updated
+        ca, cb = D[k:, k].copy(), E[k:, k].copy()
+        if k > 0:
+            ua, ub = rank2(k, n, k)
+            ca -= ua
+            cb -= ub
+        d[k] = ca[0].real
+        # (b) reflector
+        al_a, al_b, t, va_, vb_ = make_reflector(ca[1:], cb[1:])
+        ala[k], alb[k], tau[k] = al_a, al_b, t
+        D[s:, k] = va_
+        E[s:, k] = vb_
+        va = np.zeros(n, dtype=np.complex128)
+        vb = np.zeros(n, dtype=np.complex128)
+        va[s:], vb[s:] = va_, vb_
+        # (b2) Gram column: tails of the panel's earlier reflectors are read back from D, E (rows >= s)
+        for tt in range(i):
+            cj = j0 + tt
+            ga, gb = PH(D[s:, cj:cj + 1], E[s:, cj:cj + 1], va[s:], vb[s:])
+            Ga[k, tt], Gb[k, tt] = ga[0], gb[0]
+        # (c) fused pass over the lower triangles of rows/cols [s, n)
+        if k > 0:
+            for cc in range(s, n):
+                ua, ub = rank2(cc, n, cc)
+                D[cc:, cc] -= ua
+                E[cc:, cc] -= ub
+                D[cc, cc] = D[cc, cc].real
+                E[cc, cc] = 0.0
+        ya, yb = matvec_lower(D[s:, s:], E[s:, s:], va[s:], vb[s:])
+        # (d) p, g, w
+        pa = np.zeros(n, dtype=np.complex128)
+        pb = np.zeros(n, dtype=np.complex128)
+        pa[s:], pb[s:] = t * ya, t * yb
+        g = float((np.vdot(va, pa) + np.vdot(vb, pb)).real)
+        wa = pa - 0.5 * t * g * va
+        wb = pb - 0.5 * t * g * vb
+        vpa, vpb = va, vb
+    last = D[n - 1, n - 1]
+    if n > 1:
+        ua, ub = rank2(n - 1, n, n - 1)
+        last = last - ua[0]
+    d[n - 1] = last.real
+    # rows/cols of the tails: leave only what the device leaves meaningful (strictly sub-sub-diagonal)
+    return d, ala, alb, tau, D, E, Ga, Gb
+
+
 def phase_chain(ala, alb):
     """s_0 = 1, s_{k+1} = (alpha_k / |alpha_k|) s_k -- the diagonal unit-quaternion
     similarity that makes the quaternion tridiagonal real symmetric (e_k = |alpha_k|)."""

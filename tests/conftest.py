@@ -27,3 +27,11 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(params=["chain", "one_cta"])
+def reduction_path(request, monkeypatch):
+    """Small matrices (n <= 256) have two reductions: the K1-K4 multi-kernel chain and the one-CTA kernel K5
+    (small.cu, the default at that size).  ZQ_SMALL_N is read at every solve, so a test asks for either."""
+    monkeypatch.setenv("ZQ_SMALL_N", "0" if request.param == "chain" else "256")
+    return request.param

@@ -107,7 +107,7 @@ def test_k9_bisect(n):
 
 
 @pytest.mark.parametrize("n,nb", [(2, 32), (3, 2), (21, 8), (22, 4), (64, 32), (65, 32), (130, 32), (200, 64), (300, 32)])
-def test_tridiagonalisation_vs_oracle(n, nb):
+def test_tridiagonalisation_vs_oracle(n, nb, reduction_path):
     """K1-K4 chain == numpy restatement of the same formulation (different summation order only)."""
     from tests import gpu_util as G
     M = O.gen_sym(n, 200 + n)

@@ -36,7 +36,7 @@ def check_quality(M, out, eig, g=None):
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 21, 22, 23, 64, 200, 500])
-def test_testcc_golden(n):
+def test_testcc_golden(n, reduction_path):
     """BASELINE config 1 family: the reference's own test matrix (test.cc:58-78)."""
     from tests import gpu_util as G
     _, _, C = O.gen_testcc(n)
@@ -51,7 +51,7 @@ def test_testcc_golden(n):
 
 
 @pytest.mark.parametrize("key", list(SYM))
-def test_sym_golden(key):
+def test_sym_golden(key, reduction_path):
     from tests import gpu_util as G
     n, seed = (int(x) for x in key.split("_"))
     M = O.gen_sym(n, seed)
@@ -63,7 +63,7 @@ def test_sym_golden(key):
 
 
 @pytest.mark.parametrize("nb", [1, 7, 20, 64])
-def test_panel_widths(nb):
+def test_panel_widths(nb, reduction_path):
     from tests import gpu_util as G
     n = 90
     M = O.gen_sym(n, 5)
@@ -75,7 +75,7 @@ def test_panel_widths(nb):
 
 @pytest.mark.skipif(not O.RefLib.available(), reason="oracle/_ref not present")
 @pytest.mark.parametrize("n,seed", [(48, 1), (129, 2), (300, 3)])
-def test_against_reference_library(n, seed):
+def test_against_reference_library(n, seed, reduction_path):
     """identical random input through the unmodified reference (CPU) and the CUDA path; Kramers pairs
     compared as 2-D subspaces (unit-quaternion gauge freedom)."""
     from tests import gpu_util as G
@@ -100,7 +100,7 @@ def test_against_reference_library(n, seed):
         assert np.all(np.abs(sv - 1.0) <= 1e-9 * nrm / gaps[i]), (i, sv)
 
 
-def test_right_half_garbage_and_upper_triangles_ignored():
+def test_right_half_garbage_and_upper_triangles_ignored(reduction_path):
     from tests import gpu_util as G
     n = 40
     M = O.gen_sym(n, 11)
@@ -111,7 +111,7 @@ def test_right_half_garbage_and_upper_triangles_ignored():
     assert info == 0 and np.array_equal(e0[:n], e1[:n]) and np.array_equal(o0, o1)
 
 
-def test_ld2_larger_than_n2():
+def test_ld2_larger_than_n2(reduction_path):
     """the reference is wrong for ld2 != n2; this build supports it."""
     from tests import gpu_util as G
     n = 33
@@ -121,7 +121,7 @@ def test_ld2_larger_than_n2():
     assert info == 0 and np.array_equal(e0[:n], e1[:n]) and np.array_equal(o0, o1)
 
 
-def test_nan_input_reports_info():
+def test_nan_input_reports_info(reduction_path):
     from tests import gpu_util as G
     n = 30
     M = O.gen_sym(n, 13)
@@ -130,7 +130,7 @@ def test_nan_input_reports_info():
     assert info > 0                           # reference: zhbev info > 0
 
 
-def test_diagonal_and_tridiagonal_inputs():
+def test_diagonal_and_tridiagonal_inputs(reduction_path):
     from tests import gpu_util as G
     n = 50
     lam = np.linspace(-1, 1, n)
@@ -140,7 +140,7 @@ def test_diagonal_and_tridiagonal_inputs():
     check_quality(M, out, eig[:n])
 
 
-def test_clustered_spectrum():
+def test_clustered_spectrum(reduction_path):
     from tests import gpu_util as G
     n = 60
     lam = np.array([1.0] * 20 + [2.0] * 10 + list(np.linspace(3, 4, 30)))
@@ -150,7 +150,7 @@ def test_clustered_spectrum():
     check_quality(M, out, eig[:n])
 
 
-def test_values_only_and_bitwise_reproducible():
+def test_values_only_and_bitwise_reproducible(reduction_path):
     from tests import gpu_util as G
     n = 150
     M = O.gen_sym(n, 14)
@@ -187,8 +187,9 @@ def test_eigenvector_column_block():
     assert np.linalg.norm(R) <= 1e-13 * np.linalg.norm(M) * np.sqrt(nc) * 50
 
 
-def test_batched():
+def test_batched(reduction_path):
     import zquatev_b200 as z
+    z.release()
     n, batch = 20, 5
     Ms = [O.gen_sym(n, 1000 + b) for b in range(batch)]
     D = np.stack([np.asfortranarray(M).T.copy() for M in Ms])     # each slab = column-major matrix
@@ -202,12 +203,14 @@ def test_batched():
         assert O.quality(Ms[b], out, eig[b])[2] == 0.0
 
 
-def test_batched_graph_replay():
-    """More problems than lanes: the first use of a lane is eager, the second captures the solve into a CUDA
-    graph, later ones replay it.  Every problem is different, so a replay that re-used stale operands would fail."""
+def test_batched_graph_replay(reduction_path):
+    """More problems than lanes: problem 0 runs eagerly on lane 0, then every lane captures its solve into a CUDA
+    graph and host worker threads replay them.  Every problem is different, so a replay that re-used stale
+    operands would fail.  Both reductions (one-CTA K5 / multi-kernel chain) are baked into graphs this way."""
     import os
     import zquatev_b200 as z
-    n, batch = 33, 56                                  # 16 lanes -> up to 4 problems per lane; n-1 not a panel multiple
+    z.release()                                        # drop lanes (and graphs) captured with the other reduction
+    n, batch = 33, 120                                 # more problems than lanes (48 / 16); n-1 not a panel multiple
     Ms = [O.gen_sym(n, 2000 + b) for b in range(batch)]
     D = np.stack([np.asfortranarray(M).T.copy() for M in Ms])
     eig = np.zeros((batch, n))
@@ -216,8 +219,8 @@ def test_batched_graph_replay():
     g1, e1 = z.batched_stats()
     assert np.all(info == 0)
     assert (g1 - g0) + (e1 - e0) == batch
-    if os.environ.get("ZQ_BATCH_GRAPH", "1") != "0" and not os.environ.get("ZQ_BATCH_LANES"):
-        assert g1 - g0 == batch - 16, (g1 - g0, e1 - e0)   # everything after the first round of the 16 lanes is a replay
+    if os.environ.get("ZQ_BATCH_GRAPH", "1") != "0":
+        assert (g1 - g0, e1 - e0) == (batch - 1, 1)    # everything after the first problem is a replay
     for b in range(batch):
         wr = np.linalg.eigvalsh(Ms[b])[0::2]
         assert np.max(np.abs(eig[b] - wr)) <= 1e-12 * np.abs(wr).max(), b

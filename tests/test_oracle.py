@@ -139,3 +139,31 @@ def test_dc_prototype_vs_lapack(name, d, e):
     assert np.abs(w - wr).max() <= 50 * T.EPS * nrm
     assert np.linalg.norm(Tm @ Z - Z * w) / (n * nrm * T.EPS) < 2.0
     assert np.linalg.norm(Z.T @ Z - np.eye(n)) / (n * T.EPS) < 2.0
+
+
+@pytest.mark.parametrize("n,nb", [(1, 4), (2, 4), (3, 2), (7, 3), (40, 8), (65, 64), (100, 32)])
+def test_one_cta_restatement_vs_blocked(n, nb):
+    """K5's data flow (unblocked, rank-2 update fused with the next mat-vec, Gram columns read back from the
+    reflector tails) reaches the same tridiagonal, reflectors and T-factor inputs as the blocked restatement."""
+    M = O.gen_sym(n, 7)
+    D, E = M[:n, :n], M[n:, :n]
+    d0, aa0, ab0, t0, D0, E0 = K.tridiagonalise(D, E, nb)
+    d1, aa1, ab1, t1, D1, E1, Ga, Gb = K.tridiagonalise_one_cta(D, E, nb)
+    nrm = max(np.linalg.norm(M, 2), 1.0)
+    assert np.max(np.abs(d0 - d1)) <= 1e-12 * nrm
+    if n == 1:
+        return
+    e0 = np.sqrt(np.abs(aa0) ** 2 + np.abs(ab0) ** 2)
+    e1 = np.sqrt(np.abs(aa1) ** 2 + np.abs(ab1) ** 2)
+    assert np.max(np.abs(e0 - e1)) <= 1e-12 * nrm and np.max(np.abs(t0 - t1)) <= 1e-10
+    assert np.max(np.abs(np.tril(D0, -2) - np.tril(D1, -2))) <= 1e-10
+    assert np.max(np.abs(np.tril(E0, -2) - np.tril(E1, -2))) <= 1e-10
+    for j0 in range(0, n - 1, nb):                       # G[k, t] == (V^H V)[t, i] of the panel
+        kb = min(nb, n - 1 - j0)
+        P = K.phi_panel(D1, E1, j0, kb)
+        m = n - 1 - j0
+        Va, Vb = P[:m, :kb], P[m:, :kb]
+        for i in range(kb):
+            for t in range(i):
+                ga, gb = K.PH(Va[:, t:t + 1], Vb[:, t:t + 1], Va[:, i], Vb[:, i])
+                assert abs(ga[0] - Ga[j0 + i, t]) <= 1e-13 and abs(gb[0] - Gb[j0 + i, t]) <= 1e-13

@@ -104,6 +104,15 @@ void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st);
 // stand-alone K1 for tests/bench: y = M[s:,s:] v (rows < s of v must be zero)
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st);
 
+// K5 (small.cu): the whole reduction of one matrix with n <= small_n_max() in one launch of one CTA (same outputs
+// as the K1-K4 chain: d, e, tau, alpha, reflector tails in A, Gram columns G).  small_n_max() = ZQ_SMALL_N (read at
+// every solve; default and upper limit SMALL_N_MAX, 0 = always use the chain); small_prepare() opts the kernel into
+// its shared-memory size (once per device, outside any stream capture).
+constexpr int SMALL_N_MAX = 256;
+int small_n_max();
+cudaError_t small_prepare();
+void launch_tridiag_small(const PanelWs& w, cudaStream_t st);
+
 // K4 operands: L (2m x 4kb, ld 2m) and R (m x 4kb, ld m) from the panel, m = n - r0
 void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStream_t st);
 

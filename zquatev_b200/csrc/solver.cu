@@ -12,7 +12,9 @@
 #include <complex>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -142,6 +144,7 @@ static int plan_create(int n, int nb, Plan** out) {
   const size_t o_YP = take(p->yp_elems * sizeof(cplx));
   const size_t o_s = take(N * sizeof(quat)), o_bis = take((N + 8) * 8), o_info = take(256), o_eig = take(N * 8);
   cudaError_t e = cudaMalloc(&p->slab, bytes);
+  if (e == cudaSuccess) e = small_prepare();
   if (e != cudaSuccess) { delete p; return zq_cuda_fail(e, __FILE__, __LINE__); }
   char* b = p->slab;
   PanelWs& w = p->pw;
@@ -214,6 +217,11 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
   cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
+  if (n <= small_n_max()) {                 // K5: one CTA, one launch (small.cu)
+    launch_tridiag_small(w, st);
+    p->launches += 1;
+    return;
+  }
   if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
   const bool prof = g_profile && p->timing;
   if (prof && p->k1ev.size() < 2 * (size_t)n) {
@@ -704,7 +712,12 @@ int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt
   return solve_any(n2, D, ld2, eig, opt);
 }
 
-// Batched entry: see the lane machinery above.
+// Batched entry: see the lane machinery above.  The problems are handed out by an atomic counter to a few host
+// WORKER THREADS, each driving its own subset of the lanes: staging a problem costs the host ~6 MB of memcpy
+// (pageable caller memory <-> pinned lane buffers), which one thread cannot do faster than ~1.3 problems/ms --
+// slower than the GPU once the small-matrix reduction is a single launch (K5).  All lanes are captured up front
+// by the calling thread (after one eager problem on lane 0 has set the kernel attributes), so the workers only
+// copy, replay graphs and wait on their own streams.
 int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig, long long strideEig,
                          int* info) {
   if (batch < 0) return -1;
@@ -715,10 +728,15 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
   const int n = n2 / 2;
   static const int use_graph = [] { const char* e = getenv("ZQ_BATCH_GRAPH"); return e ? atoi(e) : 1; }();
   static const int lanes_env = [] { const char* e = getenv("ZQ_BATCH_LANES"); return e ? atoi(e) : 0; }();
-  const int LANES = lanes_env > 0 ? (lanes_env < 64 ? lanes_env : 64) : (use_graph ? 16 : 8);
+  static const int threads_env = [] { const char* e = getenv("ZQ_BATCH_THREADS"); return e ? atoi(e) : 0; }();
+  // a lane of the one-CTA reduction keeps one SM busy: many lanes; the multi-kernel chain fills the GPU with fewer
+  const int lanes_default = !use_graph ? 8 : (n <= small_n_max() ? 48 : 16);
+  const int LANES = lanes_env > 0 ? (lanes_env < 64 ? lanes_env : 64) : lanes_default;
   std::lock_guard<std::mutex> lk(g_mu);
   std::vector<Lane>& lanes = g_lanes;
   const int nl = batch < LANES ? batch : LANES;
+  int dev = 0;
+  ZQ_CUDA_CHECK(cudaGetDevice(&dev));
   if (g_lanes_n != n || (int)lanes.size() < nl) {
     lanes_free();
     lanes.assign(nl, Lane());
@@ -728,57 +746,100 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
       if (rc) return rc;
       ZQ_CUDA_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
       ZQ_CUDA_CHECK(cudaMalloc(&L.p->Dfull, (size_t)n2 * n2 * sizeof(cplx)));
+      L.p->dc = dc_create(n);                  // not inside a capture later
+      if (!L.p->dc) return zq_cuda_fail(cudaGetLastError(), __FILE__, __LINE__);
       ZQ_CUDA_CHECK(cudaMallocHost(&L.hinfo, sizeof(int) * 4));
       // pinned staging: a D2H copy into pageable memory would block the host and serialise the lanes
       ZQ_CUDA_CHECK(cudaMallocHost(&L.hbuf, (size_t)n2 * n2 * sizeof(cplx)));
       ZQ_CUDA_CHECK(cudaMallocHost(&L.heig, (size_t)n * sizeof(double)));
     }
   }
-  const size_t ld = (size_t)n2;
-  int worst = 0;
-  std::vector<int> pending(nl, -1);            // problem whose result sits in the lane's pinned staging
-  auto harvest = [&](int l) {
-    if (pending[l] < 0) return 0;
-    cudaError_t e = cudaStreamSynchronize(lanes[l].st);
+  std::atomic<int> next(0), worst(0), fail(0), graph_launches(0), eager_solves(0);
+  // pinned staging -> caller's arrays, after the lane's stream has drained
+  auto harvest = [&](int l, int& pb) -> int {
+    if (pb < 0) return 0;
+    Lane& L = lanes[l];
+    cudaError_t e = cudaStreamSynchronize(L.st);
     if (e != cudaSuccess) return zq_cuda_fail(e, __FILE__, __LINE__);
-    const int v = lanes[l].hinfo[0];
-    {   // pinned staging -> caller's arrays
-      const int pb = pending[l];
-      cplx* Dp = (cplx*)D + (size_t)pb * strideD;
-      for (int c = 0; c < n2; ++c) memcpy(Dp + (size_t)c * ld2, lanes[l].hbuf + (size_t)c * n2, (size_t)n2 * sizeof(cplx));
-      memcpy(eig + (size_t)pb * strideEig, lanes[l].heig, (size_t)n * sizeof(double));
-    }
-    if (info) info[pending[l]] = v;
-    if (v != 0 && worst == 0) worst = v;
-    pending[l] = -1;
+    const int v = L.hinfo[0];
+    cplx* Dp = (cplx*)D + (size_t)pb * strideD;
+    for (int c = 0; c < n2; ++c) memcpy(Dp + (size_t)c * ld2, L.hbuf + (size_t)c * n2, (size_t)n2 * sizeof(cplx));
+    memcpy(eig + (size_t)pb * strideEig, L.heig, (size_t)n * sizeof(double));
+    if (info) info[pb] = v;
+    int zero = 0;
+    if (v != 0) worst.compare_exchange_strong(zero, v);
+    pb = -1;
     return 0;
   };
-  for (int b = 0; b < batch; ++b) {
-    const int l = b % nl;
+  auto submit = [&](int l, int b) -> int {
     Lane& L = lanes[l];
-    rc = harvest(l);
-    if (rc) return rc;
-    cplx* Db = (cplx*)D + (size_t)b * strideD;
+    const cplx* Db = (const cplx*)D + (size_t)b * strideD;
     for (int c = 0; c < n; ++c) memcpy(L.hbuf + (size_t)c * n2, Db + (size_t)c * ld2, (size_t)n2 * sizeof(cplx));
-    // the first problem of a lane runs eagerly (it also creates the D&C workspace and sets the kernel attributes,
-    // which must not happen inside a capture); the second use captures, later ones replay
-    if (use_graph && !L.gexec && !L.graph_failed && L.uses >= 1) L.graph_failed = !lane_capture(L, n);
     if (L.gexec) {
       ZQ_CUDA_CHECK(cudaGraphLaunch(L.gexec, L.st));
-      ++g_batch_graph_launches;
+      ++graph_launches;
     } else {
-      rc = lane_enqueue(L, n);
-      if (rc) return rc;
-      ++g_batch_eager_solves;
+      const int r = lane_enqueue(L, n);
+      if (r) return r;
+      ++eager_solves;
     }
     ++L.uses;
-    pending[l] = b;
-  }
-  for (int l = 0; l < nl; ++l) {
-    rc = harvest(l);
+    return 0;
+  };
+  // problem 0 runs eagerly on lane 0 (first use of every kernel: attributes are set outside any capture) ...
+  int first = 0;
+  if (lanes[0].uses == 0 || !use_graph) {
+    int pb = 0;
+    rc = submit(0, 0);
     if (rc) return rc;
+    rc = harvest(0, pb);
+    if (rc) return rc;
+    first = 1;
   }
-  return worst;
+  // ... then every lane captures its solve once
+  if (use_graph)
+    for (int l = 0; l < nl; ++l)
+      if (!lanes[l].gexec && !lanes[l].graph_failed) lanes[l].graph_failed = !lane_capture(lanes[l], n);
+  next.store(first);
+  const int hw = (int)std::thread::hardware_concurrency();
+  int T = threads_env > 0 ? threads_env : 8;
+  if (hw > 1 && T > hw - 1) T = hw - 1;
+  if (!use_graph) T = 1;                       // eager enqueue stays on the calling thread
+  if (T > nl) T = nl;
+  if (T < 1) T = 1;
+  auto work = [&](int t) {
+    cudaSetDevice(dev);
+    std::vector<int> mine, pend;
+    for (int l = t; l < nl; l += T) { mine.push_back(l); pend.push_back(-1); }
+    size_t cur = 0;
+    int r = 0;
+    while (!r && !fail.load()) {
+      const int b = next.fetch_add(1);
+      if (b >= batch) break;
+      const size_t li = cur++ % mine.size();
+      r = harvest(mine[li], pend[li]);
+      if (!r) r = submit(mine[li], b);
+      if (!r) pend[li] = b;
+    }
+    for (size_t li = 0; li < mine.size(); ++li) {
+      const int r2 = harvest(mine[li], pend[li]);
+      if (!r) r = r2;
+    }
+    int zero = 0;
+    if (r) fail.compare_exchange_strong(zero, r);
+  };
+  if (T == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+  }
+  g_batch_graph_launches += graph_launches.load();
+  g_batch_eager_solves += eager_solves.load();
+  if (fail.load()) return fail.load();
+  return worst.load();
 }
 
 void zquatev_b200_batched_stats(int* graph_launches, int* eager_solves) {
