@@ -19,8 +19,10 @@
 namespace zq {
 namespace {
 
-constexpr int S_NT = 256, S_NW = S_NT / 32, S_RQ = SMALL_N_MAX / 32;
+constexpr int S_NT = 256, S_NW = S_NT / 32;
 
+// S_RQ = number of 32-row blocks a lane owns (n <= 32 S_RQ): 4 for n <= 128, 8 up to SMALL_N_MAX
+template <int S_RQ>
 __global__ void __launch_bounds__(S_NT, 1) k_tridiag_cta(PanelWs w) {
   extern __shared__ quat sm[];
   const int n = w.n, nb = w.nb;
@@ -93,7 +95,19 @@ __global__ void __launch_bounds__(S_NT, 1) k_tridiag_cta(PanelWs w) {
       const cplx* da = D + (size_t)(j0 + t) * lda;
       const cplx* ea = E + (size_t)(j0 + t) * lda;
       quat acc = qzero();
-      for (int r = s + lane; r < n; r += 32) qfma_cj(acc, qmake(da[r], ea[r]), v[r]);
+      cplx dg[S_RQ], eg[S_RQ];
+#pragma unroll
+      for (int q = 0; q < S_RQ; ++q) {                 // all loads first (predicated), then the arithmetic
+        const int r = 32 * q + lane;
+        const bool ok = r >= s && r < n;
+        dg[q] = ok ? da[r] : cmake(0, 0);
+        eg[q] = ok ? ea[r] : cmake(0, 0);
+      }
+#pragma unroll
+      for (int q = 0; q < S_RQ; ++q) {
+        const int r = 32 * q + lane;
+        if (r >= s && r < n) qfma_cj(acc, qmake(dg[q], eg[q]), v[r]);
+      }
       acc = warp_sum(acc);
       if (lane == 0) w.G[(size_t)k * nb + t] = acc;
     }
@@ -107,11 +121,21 @@ __global__ void __launch_bounds__(S_NT, 1) k_tridiag_cta(PanelWs w) {
       quat cwc = qzero(), cvc = qzero();
       if (k > 0) { cwc = qconj(wv[c]); cvc = qconj(vp[c]); }
       quat tacc = qzero();
+      // every load of the column is issued before the first dependent instruction (predicated, no branches): a
+      // branchy per-block form serialises up to S_RQ L2 round trips per column
+      cplx dv[S_RQ], ev[S_RQ];
+#pragma unroll
+      for (int q = 0; q < S_RQ; ++q) {
+        const int r = 32 * q + lane;
+        const bool ok = r >= c && r < n;
+        dv[q] = ok ? D[(size_t)r + (size_t)c * lda] : cmake(0, 0);
+        ev[q] = (ok && r > c) ? E[(size_t)r + (size_t)c * lda] : cmake(0, 0);
+      }
 #pragma unroll
       for (int q = 0; q < S_RQ; ++q) {
         const int r = 32 * q + lane;
         if (r >= c && r < n) {
-          quat m = qmake(D[(size_t)r + (size_t)c * lda], r > c ? E[(size_t)r + (size_t)c * lda] : cmake(0, 0));
+          quat m = qmake(dv[q], ev[q]);
           if (k > 0) {
             qfms(m, vp[r], cwc);
             qfms(m, wv[r], cvc);
@@ -186,11 +210,15 @@ int small_n_max() {
 }
 
 cudaError_t small_prepare() {
-  return cudaFuncSetAttribute(k_tridiag_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(SMALL_N_MAX));
+  cudaError_t e = cudaFuncSetAttribute(k_tridiag_cta<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(SMALL_N_MAX));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_tridiag_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem(128));
+  return e;
 }
 
 void launch_tridiag_small(const PanelWs& w, cudaStream_t st) {
-  k_tridiag_cta<<<1, S_NT, small_smem(w.n), st>>>(w);
+  if (w.n <= 128) k_tridiag_cta<4><<<1, S_NT, small_smem(w.n), st>>>(w);
+  else            k_tridiag_cta<8><<<1, S_NT, small_smem(w.n), st>>>(w);
 }
 
 }  // namespace zq

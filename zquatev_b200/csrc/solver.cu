@@ -731,7 +731,7 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
   static const int threads_env = [] { const char* e = getenv("ZQ_BATCH_THREADS"); return e ? atoi(e) : 0; }();
   // a lane of the one-CTA reduction keeps one SM busy: many lanes; the multi-kernel chain fills the GPU with fewer
   const int lanes_default = !use_graph ? 8 : (n <= small_n_max() ? 48 : 16);
-  const int LANES = lanes_env > 0 ? (lanes_env < 64 ? lanes_env : 64) : lanes_default;
+  const int LANES = lanes_env > 0 ? (lanes_env < 128 ? lanes_env : 128) : lanes_default;
   std::lock_guard<std::mutex> lk(g_mu);
   std::vector<Lane>& lanes = g_lanes;
   const int nl = batch < LANES ? batch : LANES;
