@@ -72,3 +72,15 @@ def test_block_cyclic_owner():
     # every rank owns the same number of blocks (+-1)
     cnt = [sum(1 for b in range(9) if b % world == r) for r in range(world)]
     assert max(cnt) - min(cnt) <= 1
+
+
+@pytest.mark.parametrize("batch,world", [(1024, 8), (1000, 8), (5, 8), (0, 4), (7, 1), (129, 2)])
+def test_batch_shards_partition(batch, world):
+    """config 5: contiguous, balanced (+-1) shards that cover the batch exactly"""
+    cover, sizes = [], []
+    for r in range(world):
+        b0, nb = zd.batch_shard(r, world, batch)
+        assert 0 <= b0 <= batch and nb >= 0
+        cover += list(range(b0, b0 + nb))
+        sizes.append(nb)
+    assert cover == list(range(batch)) and max(sizes) - min(sizes) <= 1

@@ -210,7 +210,7 @@ def test_batched_graph_replay(reduction_path):
     import os
     import zquatev_b200 as z
     z.release()                                        # drop lanes (and graphs) captured with the other reduction
-    n, batch = 33, 120                                 # more problems than lanes (48 / 16); n-1 not a panel multiple
+    n, batch = 33, 120                                 # more problems than lanes (96 / 16); n-1 not a panel multiple
     Ms = [O.gen_sym(n, 2000 + b) for b in range(batch)]
     D = np.stack([np.asfortranarray(M).T.copy() for M in Ms])
     eig = np.zeros((batch, n))

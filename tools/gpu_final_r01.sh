@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log | cut -c1-300
 timeout 200 python __graft_entry__.py > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log | cut -c1-300
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_matvec$|k_zgemm_3m|k_tridiag_cta" -c 8 -o gpurun_out/prof_r01c -f python tools/profile_kernels.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_matvec|k_zgemm_3m|k_tridiag_cta" -c 14 -o gpurun_out/prof_r01c -f python tools/profile_kernels.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_2048c.csv python bench.py --n2 2048 --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1; echo "launch list rc=$?"
 timeout 600 python bench.py > gpurun_out/bench_final_1gpu.json 2> gpurun_out/bench_final_1gpu.err; echo "bench rc=$?"; grep '^{' gpurun_out/bench_final_1gpu.json | cut -c1-3000
 timeout 200 python bench.py --impl reference > gpurun_out/bench_final_ref.json 2>&1; grep '^{' gpurun_out/bench_final_ref.json | cut -c1-500

@@ -27,3 +27,11 @@ for (ta, tb, M, N, K, lower, name) in [(0, 1, m, m, 256, 1, "trailing"), (1, 0, 
                             ctypes.byref(ms))
     fl = 8.0 * M * N * K * (0.5 if lower else 1.0)
     print(name, "ms", ms.value, "TF/s", fl / ms.value * 1e-9)
+# K5 last (one-CTA reduction of a 2n = 512 problem): a solve below n = 1024 switches the GEMMs to the 4-product kernel
+import zquatev_b200 as z
+from bench import make_input
+ns = 256
+ws = torch.empty((2 * ns, 2 * ns), dtype=torch.complex128, device="cuda")
+ws[:ns].copy_(make_input(ns, torch.device("cuda", 0)))
+es = torch.zeros(ns, dtype=torch.float64, device="cuda")
+print("k5 solve info", z.zquatev_device(2 * ns, ws.data_ptr(), 2 * ns, es.data_ptr(), sync=True), z.last_phases())

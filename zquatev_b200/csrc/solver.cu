@@ -730,7 +730,7 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
   static const int lanes_env = [] { const char* e = getenv("ZQ_BATCH_LANES"); return e ? atoi(e) : 0; }();
   static const int threads_env = [] { const char* e = getenv("ZQ_BATCH_THREADS"); return e ? atoi(e) : 0; }();
   // a lane of the one-CTA reduction keeps one SM busy: many lanes; the multi-kernel chain fills the GPU with fewer
-  const int lanes_default = !use_graph ? 8 : (n <= small_n_max() ? 48 : 16);
+  const int lanes_default = !use_graph ? 8 : (n <= small_n_max() ? 96 : 16);   // measured: profiles/r01_probe_batched.jsonl
   const int LANES = lanes_env > 0 ? (lanes_env < 128 ? lanes_env : 128) : lanes_default;
   std::lock_guard<std::mutex> lk(g_mu);
   std::vector<Lane>& lanes = g_lanes;
@@ -802,7 +802,7 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
       if (!lanes[l].gexec && !lanes[l].graph_failed) lanes[l].graph_failed = !lane_capture(lanes[l], n);
   next.store(first);
   const int hw = (int)std::thread::hardware_concurrency();
-  int T = threads_env > 0 ? threads_env : 8;
+  int T = threads_env > 0 ? threads_env : 12;
   if (hw > 1 && T > hw - 1) T = hw - 1;
   if (!use_graph) T = 1;                       // eager enqueue stays on the calling thread
   if (T > nl) T = nl;

@@ -15,6 +15,15 @@ def column_block(rank: int, world: int, n: int):
     return col0, max(0, min(per, n - col0))
 
 
+def batch_shard(rank: int, world: int, batch: int):
+    """Problems [b0, b0 + nb) of a batch of independent small matrices that `rank` solves (BASELINE
+    config 5: one batch shard per GPU, no collective on the data path): contiguous shards whose sizes
+    differ by at most one, so the caller's arrays are sliced without copies."""
+    base, extra = divmod(batch, world)
+    b0 = rank * base + min(rank, extra)
+    return b0, base + (1 if rank < extra else 0)
+
+
 def owner_of_column(k: int, world: int, nb: int = 64) -> int:
     """Rank that owns column k of (D; E) in the 1-D block-cyclic layout of the reduction."""
     return (k // nb) % world
@@ -63,3 +72,15 @@ def init_from_torch(group=None):
 
 def finalize():
     api.lib().zquatev_b200_dist_finalize()
+
+
+def zquatev_batched_sharded(D, eig, group=None):
+    """Config 5 across the ranks of a torch.distributed group: every rank holds the same (batch, n2, n2) / (batch, n)
+    host arrays and solves only its own shard in place through `zquatev_batched` (independent problems: no data-path
+    collective).  Returns (b0, nb, info) of the local shard; gathering the shards is the caller's choice."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    b0, nb = batch_shard(rank, world, D.shape[0])
+    info = api.zquatev_batched(D[b0:b0 + nb], eig[b0:b0 + nb]) if nb > 0 else None
+    return b0, nb, info
