@@ -71,7 +71,13 @@ int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt
 
 /* `batch` independent problems of the same size (BASELINE config 5): problem b uses
  * D + b*strideD (complex elements) and eig + b*strideEig; info[b] receives its return code.
- * Host pointers.  The reference has no batched entry -- its callers loop over zquatev().      */
+ * Host pointers.  The reference has no batched entry -- its callers loop over zquatev().
+ * Inside: up to 96 lanes (stream + workspace + pinned staging), each replaying a CUDA graph of its
+ * whole solve; a few host worker threads stage the problems and hand them out (ZQ_BATCH_LANES,
+ * ZQ_BATCH_THREADS, ZQ_BATCH_GRAPH).  For n <= 256 the reduction is ONE launch of a one-CTA kernel
+ * (ZQ_SMALL_N), so the lanes run on different SMs side by side.  The call returns when every
+ * problem is back in the caller's arrays.  Across GPUs the batch is sharded by the caller, one
+ * contiguous shard per process (zquatev_b200/dist.py: batch_shard) -- no collective.            */
 int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD, double* eig,
                          long long strideEig, int* info);
 
