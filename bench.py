@@ -243,6 +243,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
     phases = z.last_phases()
+    if world > 1:
+        phases["gather"] = z.last_gather_ms()                    # NCCL gather of the eigenvector shards (inside "backtransform")
 
     # ---- sanity of the last result (cheap, outside the timed region): sum(eig) = trace(A) ----
     tr = torch.diagonal(left0[:, :n]).real.sum().item()

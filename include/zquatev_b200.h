@@ -111,6 +111,9 @@ void zquatev_b200_set_profiling(int on);
 /* Milliseconds spent in the trailing-update GEMMs (K4) of the last PROFILED single-GPU solve (event pair
  * around each of the n/nb launches); 0 when profiling was off.                                         */
 double zquatev_b200_last_trailing_ms(void);
+/* Milliseconds of the NCCL gather of the eigenvector column shards at the end of the last collective
+ * (dist = 1) solve -- part of phase [3]; 0 for single-GPU solves.                                       */
+double zquatev_b200_last_gather_ms(void);
 
 /* Library build info, e.g. "zquatev_b200 0.1 sm_100a nb=32".                                   */
 const char* zquatev_b200_version(void);

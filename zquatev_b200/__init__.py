@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     ZqOptions,
     batched_stats,
     last_phases,
+    last_gather_ms,
     last_trailing_ms,
     lib,
     release,
@@ -25,5 +26,5 @@ from .api import (  # noqa: F401
     zquatev_device,
 )
 
-__all__ = ["zquatev", "zquatev_device", "zquatev_batched", "batched_stats", "last_phases", "last_trailing_ms", "set_profiling", "release", "version",
+__all__ = ["zquatev", "zquatev_device", "zquatev_batched", "batched_stats", "last_phases", "last_gather_ms", "last_trailing_ms", "set_profiling", "release", "version",
            "lib", "LIB_PATH", "ZqOptions"]

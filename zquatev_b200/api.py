@@ -33,6 +33,7 @@ SYMBOLS = {
     "zquatev_b200_last_phases": (_I, [_P]),
     "zquatev_b200_set_profiling": (None, [_I]),
     "zquatev_b200_last_trailing_ms": (_D, []),
+    "zquatev_b200_last_gather_ms": (_D, []),
     "zquatev_b200_version": (ctypes.c_char_p, []),
     "zq_test_matvec": (_I, [_I, _I, _P, _LL, _P, _P, _I, _P]),
     "zq_test_zgemm": (_I, [_I, _I, _I, _I, _I, _P, _P, _LL, _P, _LL, _P, _P, _LL, _I, _I, _P]),
@@ -125,6 +126,11 @@ def last_phases():
 def last_trailing_ms() -> float:
     """device milliseconds of the trailing-update GEMMs of the last profiled single-GPU solve"""
     return float(lib().zquatev_b200_last_trailing_ms())
+
+
+def last_gather_ms() -> float:
+    """device milliseconds of the NCCL gather of the eigenvector shards in the last collective solve (0: single GPU)"""
+    return float(lib().zquatev_b200_last_gather_ms())
 
 
 def set_profiling(on: bool):

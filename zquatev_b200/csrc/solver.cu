@@ -46,6 +46,8 @@ struct Plan {
   cplx* Dfull = nullptr;     // host-pointer mode staging, 2n x 2n
   double* eig_dev = nullptr;
   cudaEvent_t ev[6] = {};
+  cudaEvent_t ev_gather = nullptr;   // multi-GPU: recorded before the NCCL gather of the eigenvector shards
+  double gather_ms = 0;
   std::vector<cudaEvent_t> k1ev;
   std::vector<cudaEvent_t> k4ev;   // profiling: event pair around every trailing-update GEMM
   double k4_ms = 0;
@@ -106,6 +108,7 @@ static void plan_free(Plan* p) {
   if (p->Dfull) cudaFree(p->Dfull);
   if (p->dc) dc_destroy(p->dc);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+  if (p->ev_gather) cudaEventDestroy(p->ev_gather);
   for (auto& e : p->k1ev) cudaEventDestroy(e);
   for (auto& e : p->k4ev) cudaEventDestroy(e);
   delete p;
@@ -158,6 +161,7 @@ static int plan_create(int n, int nb, Plan** out) {
   p->Y = (cplx*)(b + o_Y); p->TY = (cplx*)(b + o_TY); p->YP = (cplx*)(b + o_YP); p->s = (quat*)(b + o_s); p->bis = (double*)(b + o_bis);
   p->info_dev = (int*)(b + o_info); p->eig_dev = (double*)(b + o_eig);
   for (auto& ev : p->ev) cudaEventCreate(&ev);
+  cudaEventCreate(&p->ev_gather);
   *out = p;
   return 0;
 }
@@ -465,6 +469,7 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   w.A = Dfull;
   w.lda = ld;
   p->launches = 0;
+  p->gather_ms = -1.0;
   zgemm_allow_3m(n >= 1024);
   cudaMemsetAsync(p->info_dev, 0, sizeof(int), st);
   if (p->timing) cudaEventRecord(p->ev[1], st);
@@ -507,6 +512,7 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     backtransform(p, X + (size_t)col0 * ld, ld, ncols, st);
     launch_swap_pairing(n, ncols, Dfull + (size_t)col0 * ld, ld, st);
     if (dist && gather) {                       // every rank ends with all 2n columns
+      if (p->timing) { cudaEventRecord(p->ev_gather, st); p->gather_ms = 0.0; }
       const int per = (n + g_world - 1) / g_world;
       if (n % g_world == 0) {                   // equal blocks: in-place all-gather of each half
         cplx* L = Dfull;
@@ -559,6 +565,12 @@ static void collect_phases(Plan* p, bool host_mode) {
     }
     cudaGetLastError();
     p->k4_ms = t4;
+  }
+  if (p->gather_ms >= 0.0) {                  // the last solve gathered: time from the end of the local pairing to ev[4]
+    p->gather_ms = (cudaEventElapsedTime(&t, p->ev_gather, p->ev[4]) == cudaSuccess) ? t : 0.0;
+    cudaGetLastError();
+  } else {
+    p->gather_ms = 0.0;
   }
   ms[7] = (double)p->launches;
 }
@@ -660,6 +672,7 @@ struct Lane {
 };
 std::vector<Lane> g_lanes;
 int g_lanes_n = -1;
+bool g_lanes_small = false;     // reduction baked into the lanes' graphs: K5 (true) or the K1-K4 chain
 int g_batch_graph_launches = 0, g_batch_eager_solves = 0;
 
 void lanes_free() {
@@ -737,10 +750,12 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
   const int nl = batch < LANES ? batch : LANES;
   int dev = 0;
   ZQ_CUDA_CHECK(cudaGetDevice(&dev));
-  if (g_lanes_n != n || (int)lanes.size() < nl) {
+  const bool small_now = n <= small_n_max();
+  if (g_lanes_n != n || (int)lanes.size() < nl || g_lanes_small != small_now) {   // (graphs bake the reduction in)
     lanes_free();
     lanes.assign(nl, Lane());
     g_lanes_n = n;
+    g_lanes_small = small_now;
     for (auto& L : lanes) {
       rc = plan_create(n, DEFAULT_NB, &L.p);
       if (rc) return rc;
@@ -896,6 +911,11 @@ int zquatev_b200_last_phases(double ms[8]) {
 }
 
 void zquatev_b200_set_profiling(int on) { g_profile = on != 0; }
+
+double zquatev_b200_last_gather_ms(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_plan ? g_plan->gather_ms : 0.0;
+}
 
 double zquatev_b200_last_trailing_ms(void) {
   std::lock_guard<std::mutex> lk(g_mu);
