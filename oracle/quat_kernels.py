@@ -298,6 +298,48 @@ def backtransform(D, E, tau, Xa, Xb, nb):
     return X[:n], X[n:]
 
 
+def backtransform_paired(D, E, tau, Xa, Xb, nb):
+    """K6 with two panels merged per step (solver.cu `backtransform`, ZQ_BT_PAIR=1): for panels j < j' applied
+    together,  H_j H_j' = I - [P_j P_j'] [[T_j, -T_j (P_j^H P_j') T_j'], [0, T_j']] [P_j P_j']^H,
+    where P_j' is zero-padded to the rows of P_j.  The K = 4 nb update GEMM visits every C tile half as often."""
+    n = D.shape[0]
+    X = np.vstack([Xa, Xb])
+    starts = list(range(0, n - 1, nb))
+    i = len(starts) - 1
+    while i >= 0:
+        if i >= 1:
+            ja, jb = starts[i - 1], starts[i]
+            ka, kbb = min(nb, n - 1 - ja), min(nb, n - 1 - jb)
+            ma, mb = n - 1 - ja, n - 1 - jb
+            Pa = phi_panel(D, E, ja, ka)
+            Pb0 = phi_panel(D, E, jb, kbb)
+            Pb = np.zeros((2 * ma, 2 * kbb), dtype=np.complex128)
+            Pb[ma - mb:ma] = Pb0[:mb]                # a-rows, shifted down by jb - ja
+            Pb[2 * ma - mb:] = Pb0[mb:]              # b-rows
+            Ta = tfactor(Pa, tau[ja:ja + ka])
+            Tb = tfactor(Pb0, tau[jb:jb + kbb])
+            S = c(Pa).T @ Pb
+            Pc = np.hstack([Pa, Pb])
+            T12 = np.zeros((2 * (ka + kbb), 2 * (ka + kbb)), dtype=np.complex128)
+            T12[:2 * ka, :2 * ka] = Ta
+            T12[2 * ka:, 2 * ka:] = Tb
+            T12[:2 * ka, 2 * ka:] = -Ta @ (S @ Tb)
+            rows = np.concatenate([np.arange(ja + 1, n), n + np.arange(ja + 1, n)])
+            Y = c(Pc).T @ X[rows]
+            X[rows] -= Pc @ (T12 @ Y)
+            i -= 2
+        else:
+            j0 = starts[0]
+            kb = min(nb, n - 1 - j0)
+            P = phi_panel(D, E, j0, kb)
+            T = tfactor(P, tau[j0:j0 + kb])
+            rows = np.concatenate([np.arange(j0 + 1, n), n + np.arange(j0 + 1, n)])
+            Y = c(P).T @ X[rows]
+            X[rows] -= P @ (T @ Y)
+            i -= 1
+    return X[:n], X[n:]
+
+
 def solve(M, nb=8, tridiag_solver=None):
     """Whole B200 formulation on the CPU: returns (eig, out) like ts::zquatev."""
     n = M.shape[0] // 2

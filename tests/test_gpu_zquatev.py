@@ -269,3 +269,20 @@ def test_properties_at_scale_device_resident(n):
     U, W = V[:n, :n], V[n:, :n]
     assert torch.equal(V[:n, n:], -W.conj()) and torch.equal(V[n:, n:], U.conj())
     assert bool(torch.all(eig[1:] >= eig[:-1]))
+
+
+@pytest.mark.skipif(os.environ.get("ZQ_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="experimental code path, not validated on a GPU yet (set ZQ_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("n,nb", [(130, 64), (200, 64), (500, 64), (300, 20), (90, 7), (1024, 64)])
+def test_experimental_paired_backtransform(n, nb, monkeypatch):
+    """ZQ_BT_PAIR=1: two panels merged per back-transformation step must give the same answer as panel by panel."""
+    from tests import gpu_util as G
+    M = O.gen_sym(n, 77)
+    monkeypatch.setenv("ZQ_SMALL_N", "0")
+    monkeypatch.setenv("ZQ_BT_PAIR", "0")
+    e0, o0, i0 = G.solve_host(M, nb=nb)
+    monkeypatch.setenv("ZQ_BT_PAIR", "1")
+    e1, o1, i1 = G.solve_host(M, nb=nb)
+    assert i0 == 0 and i1 == 0 and np.array_equal(e0[:n], e1[:n])
+    assert np.max(np.abs(o0 - o1)) <= 1e-12
+    check_quality(M, o1, e1[:n])

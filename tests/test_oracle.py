@@ -167,3 +167,17 @@ def test_one_cta_restatement_vs_blocked(n, nb):
             for t in range(i):
                 ga, gb = K.PH(Va[:, t:t + 1], Vb[:, t:t + 1], Va[:, i], Vb[:, i])
                 assert abs(ga[0] - Ga[j0 + i, t]) <= 1e-13 and abs(gb[0] - Gb[j0 + i, t]) <= 1e-13
+
+
+@pytest.mark.parametrize("n,nb", [(2, 4), (5, 2), (9, 4), (33, 8), (70, 16), (64, 64), (130, 32)])
+def test_paired_backtransform_restatement(n, nb):
+    """two panels merged per step (T12 = [[Ta, -Ta Pa^H Pb Tb], [0, Tb]]) == panel-by-panel back-transformation"""
+    rng = np.random.default_rng(n)
+    M = O.gen_sym(n, 3)
+    _, _, _, tau, Df, Ef = K.tridiagonalise(M[:n, :n], M[n:, :n], nb)
+    Xa = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    Xb = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    a0, b0 = K.backtransform(Df, Ef, tau, Xa.copy(), Xb.copy(), nb)
+    a1, b1 = K.backtransform_paired(Df, Ef, tau, Xa.copy(), Xb.copy(), nb)
+    scale = max(np.abs(a0).max(), np.abs(b0).max())
+    assert np.abs(a0 - a1).max() <= 1e-13 * scale and np.abs(b0 - b1).max() <= 1e-13 * scale

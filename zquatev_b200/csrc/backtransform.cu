@@ -31,6 +31,42 @@ __global__ void __launch_bounds__(256) k_build_phi(PanelWs w, int j0, int kb, cp
   P[m + rr + (size_t)(kb + t) * ld] = cconj(va);
 }
 
+// Same as k_build_phi for a panel that is merged with an EARLIER panel (two-panel back-transformation, solver.cu):
+// the operand has m_op rows per half (those of the earlier panel), this panel starts `row_off` rows further down,
+// the rows above it are zero.
+__global__ void __launch_bounds__(256) k_build_phi_padded(PanelWs w, int j0, int kb, cplx* P, int m_op, int row_off) {
+  const int n = w.n;
+  const int t = blockIdx.y;
+  const int ro = blockIdx.x * 256 + threadIdx.x;      // row inside the operand's half
+  if (ro >= m_op) return;
+  const int rr = ro - row_off;                        // row inside this panel's own half (row j0+1+rr of the matrix)
+  cplx va = cmake(0, 0), vb = cmake(0, 0);
+  if (rr == t) va = cmake(1, 0);
+  else if (rr > t) {
+    const size_t r = (size_t)(j0 + 1 + rr), k = (size_t)(j0 + t);
+    va = w.A[r + k * w.lda];
+    vb = w.A[n + r + k * w.lda];
+  }
+  const size_t ld = 2 * (size_t)m_op;
+  P[ro + (size_t)t * ld] = va;
+  P[m_op + ro + (size_t)t * ld] = vb;
+  P[ro + (size_t)(kb + t) * ld] = cneg(cconj(vb));
+  P[m_op + ro + (size_t)(kb + t) * ld] = cconj(va);
+}
+
+// T12 (Kc x Kc, Kc = 2ka + 2kb, ld Kc) <- [[Ta, 0], [0, Tb]]; the upper-right block is filled by a GEMM afterwards
+__global__ void __launch_bounds__(256) k_assemble_T12(const cplx* __restrict__ Ta, int ka2, const cplx* __restrict__ Tb, int kb2,
+                                                      cplx* __restrict__ T12) {
+  const int Kc = ka2 + kb2;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < Kc * Kc; idx += gridDim.x * 256) {
+    const int r = idx % Kc, c = idx / Kc;
+    cplx v = cmake(0, 0);
+    if (r < ka2 && c < ka2) v = Ta[r + (size_t)c * ka2];
+    else if (r >= ka2 && c >= ka2) v = Tb[(r - ka2) + (size_t)(c - ka2) * kb2];
+    T12[idx] = v;
+  }
+}
+
 // T = Phi(T_q), T_q upper triangular quaternion kb x kb:
 //   T_q[i,i] = tau_i ;  T_q[0:i, i] = -tau_i T_q[0:i,0:i] g_i ,  g_i = V[:, 0:i]^H v_i  (saved in G)
 // so that H_{j0} ... H_{j0+kb-1} = I - V T_q V^H (forward, column-wise; zlarft analogue).
@@ -166,6 +202,16 @@ void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st
   const int m = w.n - 1 - j0;
   dim3 g((m + 255) / 256, kb);
   k_build_phi<<<g, 256, 0, st>>>(w, j0, kb, P);
+}
+
+void launch_build_phi_padded(const PanelWs& w, int j0, int kb, cplx* P, int m_op, int row_off, cudaStream_t st) {
+  dim3 g((m_op + 255) / 256, kb);
+  k_build_phi_padded<<<g, 256, 0, st>>>(w, j0, kb, P, m_op, row_off);
+}
+
+void launch_assemble_T12(const cplx* Ta, int ka2, const cplx* Tb, int kb2, cplx* T12, cudaStream_t st) {
+  const int Kc = ka2 + kb2;
+  k_assemble_T12<<<(Kc * Kc + 255) / 256, 256, 0, st>>>(Ta, ka2, Tb, kb2, T12);
 }
 
 void launch_build_T_all(const PanelWs& w, cplx* Tall, cudaStream_t st) {

@@ -144,6 +144,10 @@ void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx
 // K6 helpers (backtransform.cu)
 //   P = Phi(V) of panel [j0, j0+kb): (2m x 2kb), ld 2m, m = n-1-j0 ; rows [0,m) <-> a-part rows j0+1..
 void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st);
+//   two-panel form (ZQ_BT_PAIR): Phi(V) of a panel zero-padded to the m_op rows (per half) of the earlier panel it is
+//   merged with, and T12 = [[Ta, 0], [0, Tb]] (the off-diagonal block -Ta (Pa^H Pb) Tb is added by GEMMs)
+void launch_build_phi_padded(const PanelWs& w, int j0, int kb, cplx* P, int m_op, int row_off, cudaStream_t st);
+void launch_assemble_T12(const cplx* Ta, int ka2, const cplx* Tb, int kb2, cplx* T12, cudaStream_t st);
 //   T of every panel (panel j at Tall + j * 4 nb^2: 2kb x 2kb complex, ld 2kb) from saved Gram columns G and tau
 void launch_build_T_all(const PanelWs& w, cplx* Tall, cudaStream_t st);
 //   phase chain s (n quats) from alpha; X0 = diag(s) Z[:, perm]

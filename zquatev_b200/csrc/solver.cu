@@ -38,6 +38,7 @@ struct Plan {
   char* slab = nullptr;
   PanelWs pw{};
   cplx *L = nullptr, *R = nullptr, *P = nullptr, *T = nullptr, *Y = nullptr, *TY = nullptr, *YP = nullptr;
+  cplx *T12 = nullptr, *S12 = nullptr, *ST = nullptr;   // two-panel back-transformation (ZQ_BT_PAIR)
   size_t yp_elems = 0;       // capacity of YP (split-K partial products of Y = Phi(V)^H X)
   quat* s = nullptr;
   double* bis = nullptr;
@@ -141,8 +142,11 @@ static int plan_create(int n, int nb, Plan** out) {
   const size_t o_d = take(N * 8), o_e = take(N * 8), o_tau = take(N * 8), o_al = take(N * sizeof(quat));
   const size_t o_G = take(N * nb * sizeof(quat));
   const size_t o_L = take(2 * N * 4 * nb * sizeof(cplx)), o_R = take(N * 4 * nb * sizeof(cplx));
-  const size_t o_P = take(2 * N * 2 * nb * sizeof(cplx)), o_T = take((size_t)cdiv(n, nb) * 4 * nb * nb * sizeof(cplx));   // T of every panel
-  const size_t o_Y = take((size_t)2 * nb * N * sizeof(cplx)), o_TY = take((size_t)2 * nb * N * sizeof(cplx));
+  // P, Y, TY are sized for TWO merged panels (ZQ_BT_PAIR); T12 / S12 / ST hold the merged T factor and its cross term
+  const size_t o_P = take(2 * N * 4 * nb * sizeof(cplx)), o_T = take((size_t)cdiv(n, nb) * 4 * nb * nb * sizeof(cplx));   // T of every panel
+  const size_t o_T12 = take((size_t)16 * nb * nb * sizeof(cplx)), o_S12 = take((size_t)4 * nb * nb * sizeof(cplx));
+  const size_t o_ST = take((size_t)4 * nb * nb * sizeof(cplx));
+  const size_t o_Y = take((size_t)4 * nb * N * sizeof(cplx)), o_TY = take((size_t)4 * nb * N * sizeof(cplx));
   p->yp_elems = (size_t)YP_PARTS * 2 * nb * N;
   const size_t o_YP = take(p->yp_elems * sizeof(cplx));
   const size_t o_s = take(N * sizeof(quat)), o_bis = take((N + 8) * 8), o_info = take(256), o_eig = take(N * 8);
@@ -158,6 +162,7 @@ static int plan_create(int n, int nb, Plan** out) {
   w.d = (double*)(b + o_d); w.e = (double*)(b + o_e); w.tau = (double*)(b + o_tau); w.alpha = (quat*)(b + o_al);
   w.G = (quat*)(b + o_G);
   p->L = (cplx*)(b + o_L); p->R = (cplx*)(b + o_R); p->P = (cplx*)(b + o_P); p->T = (cplx*)(b + o_T);
+  p->T12 = (cplx*)(b + o_T12); p->S12 = (cplx*)(b + o_S12); p->ST = (cplx*)(b + o_ST);
   p->Y = (cplx*)(b + o_Y); p->TY = (cplx*)(b + o_TY); p->YP = (cplx*)(b + o_YP); p->s = (quat*)(b + o_s); p->bis = (double*)(b + o_bis);
   p->info_dev = (int*)(b + o_info); p->eig_dev = (double*)(b + o_eig);
   for (auto& ev : p->ev) cudaEventCreate(&ev);
@@ -411,6 +416,65 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   return 0;
 }
 
+// split-K geometry of Y = P^H X (M x ncols, K = m per segment, two segments): enough K-chunks for >= 8 waves
+static SplitK bt_splitk(const Plan* p, int M, int ncols, int m, size_t segA, size_t segB) {
+  const size_t ypart = (size_t)M * ncols;
+  const int ctas1 = ((M + 63) / 64) * 2 * ((ncols + 63) / 64);
+  int chunks = (8 * 444 + 2 * ctas1 - 1) / (2 * ctas1);
+  const int cap_mem = (int)(p->yp_elems / ypart / 2), cap_k = m / 256;
+  if (chunks > cap_mem) chunks = cap_mem;
+  if (chunks > YP_MAX_CHUNKS) chunks = YP_MAX_CHUNKS;
+  if (chunks > cap_k) chunks = cap_k;
+  if (chunks < 1) chunks = 1;
+  SplitK sk;
+  sk.kc = (((m + chunks - 1) / chunks) + 7) & ~7;
+  sk.chunks = (m + sk.kc - 1) / sk.kc;
+  sk.segA = segA;
+  sk.segB = segB;
+  return sk;
+}
+
+// EXPERIMENTAL (ZQ_BT_PAIR=1, off by default; oracle: quat_kernels.backtransform_paired): panels ja < jb applied in one
+// step,  H_ja H_jb = I - [Pa Pb] [[Ta, -Ta (Pa^H Pb) Tb], [0, Tb]] [Pa Pb]^H  with Pb zero-padded to the rows of Pa.
+// The update GEMM then has K = 4 nb, so every C tile of X is loaded and stored half as often per flop.
+static void backtransform_pair(Plan* p, cplx* X, size_t ldx, int ncols, int ja, int jb, cudaStream_t st) {
+  const PanelWs& w = p->pw;
+  const int n = w.n, nb = w.nb;
+  const int ka = (nb < n - 1 - ja) ? nb : n - 1 - ja, kb = (nb < n - 1 - jb) ? nb : n - 1 - jb;
+  const int m = n - 1 - ja, off = jb - ja;
+  const int Ka = 2 * ka, Kb = 2 * kb, Kc = Ka + Kb;
+  const size_t ldp = 2 * (size_t)m;
+  cplx* Pa = p->P;
+  cplx* Pb = p->P + (size_t)Ka * ldp;
+  const cplx* Ta = p->T + (size_t)(ja / nb) * 4 * nb * nb;
+  const cplx* Tb = p->T + (size_t)(jb / nb) * 4 * nb * nb;
+  cplx* Xa = X + (size_t)(ja + 1);
+  launch_build_phi(w, ja, ka, Pa, st);
+  launch_build_phi_padded(w, jb, kb, Pb, m, off, st);
+  // S = Pa^H Pb  (Ka x Kb), K = m over the a-rows and the b-rows
+  {
+    const SplitK sk = bt_splitk(p, Ka, Kb, m, (size_t)m, (size_t)m);
+    const size_t spart = (size_t)Ka * Kb;
+    launch_zgemm_splitk(1, 0, Ka, Kb, m, Pa, ldp, Pb, ldp, p->YP, (size_t)Ka, spart, 2, sk, st);
+    launch_sum_parts(spart, 2 * sk.chunks, p->YP, spart, p->S12, st);
+  }
+  // T12 = [[Ta, -Ta S Tb], [0, Tb]]
+  launch_assemble_T12(Ta, Ka, Tb, Kb, p->T12, st);
+  launch_zgemm(0, 0, Ka, Kb, Kb, cmake(1, 0), p->S12, (size_t)Ka, Tb, (size_t)Kb, cmake(0, 0), p->ST, (size_t)Ka, 0, 1, 0, 0, 0, st);
+  launch_zgemm(0, 0, Ka, Kb, Ka, cmake(-1, 0), Ta, (size_t)Ka, p->ST, (size_t)Ka, cmake(0, 0), p->T12 + (size_t)Ka * Kc, (size_t)Kc, 0, 1, 0, 0,
+               0, st);
+  // Y = [Pa Pb]^H X, TY = T12 Y, X -= [Pa Pb] TY
+  {
+    const SplitK sk = bt_splitk(p, Kc, ncols, m, (size_t)m, (size_t)n);
+    const size_t ypart = (size_t)Kc * ncols;
+    launch_zgemm_splitk(1, 0, Kc, ncols, m, p->P, ldp, Xa, ldx, p->YP, (size_t)Kc, ypart, 2, sk, st);
+    launch_sum_parts(ypart, 2 * sk.chunks, p->YP, ypart, p->Y, st);
+  }
+  launch_zgemm(0, 0, Kc, ncols, Kc, cmake(1, 0), p->T12, (size_t)Kc, p->Y, (size_t)Kc, cmake(0, 0), p->TY, (size_t)Kc, 0, 1, 0, 0, 0, st);
+  launch_zgemm(0, 0, m, ncols, Kc, cmake(-1, 0), p->P, ldp, p->TY, (size_t)Kc, cmake(1, 0), Xa, ldx, 0, 2, (size_t)m, 0, (size_t)n, st);
+  p->launches += 11;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K6: X <- H_0 ... H_{n-2} X, X = stacked (Xa; Xb), 2n x n, leading dimension ldx
 // ---------------------------------------------------------------------------------------------
@@ -421,7 +485,14 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
   const int last = ((n - 2) / nb) * nb;
   launch_build_T_all(w, p->T, st);
   p->launches += 1;
+  const char* pe = getenv("ZQ_BT_PAIR");                 // read at every solve (tests switch it)
+  const bool pair = pe && atoi(pe) != 0;
   for (int j0 = last; j0 >= 0; j0 -= nb) {
+    if (pair && j0 >= nb) {                              // merge this panel with the one before it
+      backtransform_pair(p, X, ldx, ncols, j0 - nb, j0, st);
+      j0 -= nb;
+      continue;
+    }
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
     const int m = n - 1 - j0;
     launch_build_phi(w, j0, kb, p->P, st);
