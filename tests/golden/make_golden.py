@@ -37,7 +37,7 @@ def main():
         print("testcc", n, out[str(n)]["eig"][0], out[str(n)]["residual"], out[str(n)]["orthogonality"])
     json.dump(out, open(os.path.join(HERE, "testcc_eigs.json"), "w"))
     out = {}
-    for n, seed in [(5, 32), (33, 33), (100, 34), (257, 32)]:
+    for n, seed in [(5, 32), (33, 33), (100, 34), (257, 32), (256, 1000)]:   # (256, 1000): first problem of the config-5 batch
         M = O.gen_sym(n, seed)
         out[f"{n}_{seed}"] = record(M, ref)
         print("sym", n, seed, out[f"{n}_{seed}"]["eig"][0], out[f"{n}_{seed}"]["residual"])
