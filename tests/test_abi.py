@@ -75,3 +75,18 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace(
                     "oracle/.", ""), f
+
+
+def test_headers_compile_standalone(tmp_path):
+    """include/zquatev_b200.h is plain C (no torch / CUDA types in the signatures); include/zquatev.h is the C++
+    declaration of the reference symbol -- both must compile on their own with the host compilers."""
+    inc = os.path.join(ROOT, "include")
+    c = tmp_path / "t.c"
+    c.write_text('#include "zquatev_b200.h"\nint main(void) { zq_options o = {0}; (void)o; return zquatev_b200_version() == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(c)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cc = tmp_path / "t.cc"
+    cc.write_text('#include "zquatev.h"\n#include "zquatev_b200.h"\n'
+                  'int f(int n2, std::complex<double>* D, double* e) { return ts::zquatev(n2, D, n2, e); }\n')
+    r = subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(cc)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
