@@ -14,9 +14,16 @@ N > 1   : strong scaling (the problem is fixed).  One collective solve: D and E 
           all-reduce of the partial mat-vec), trailing update on owned blocks only, back-transformation
           sharded by eigenvector columns, result gathered on every rank; the tridiagonal D&C is
           replicated.
---impl reference : the UNMODIFIED reference ts::zquatev built in oracle/_ref, timed on the host
-          cores on a bounded sample (2n = 2048) and scaled by n^3 to the workload (SURVEY.md 8d:
-          a real 2n=32768 CPU run takes ~12 h).
+quality : after the timed loop (outside it) the result of the LAST timed solve is checked on the device at the
+          full size, on every N: residual ||MV-VL||_F/(N||M||_F eps), orthogonality ||V^H V-I||_F/(N eps), exact
+          quaternion pairing, trace, sum of squares, ascending order (the checks of test.cc:104-112); for N > 1
+          also that all ranks hold bit-identical eigenvalues and that they agree with a single-GPU solve of the
+          same matrix within 1e-12 ||A||.  The run FAILS (assert) if res >= 0.5, orth >= 1.5 or pairing != 0.
+--impl reference : the UNMODIFIED reference ts::zquatev built in oracle/_ref on the host cores.  Each step times a
+          bounded sample (2n = 2048); once per run ts::zquatev AND LAPACK zheev on the 2n matrix (test.cc:84-102)
+          are timed at n = 500, 1024, 2048 (zheev: 500, 1024), power laws a*n^p are fitted and the value is
+          EXTRAPOLATED to the workload with the fitted exponent (a real 2n=32768 CPU run takes
+          hours).  The same three-point measurement is the `cpu_baseline` of the GPU arm at N = 1.
 """
 from __future__ import annotations
 
@@ -36,6 +43,57 @@ sys.path.insert(0, ROOT)
 METRIC = "2n=%d eigvals+vecs time-to-solution"
 GEMM_EXEC = 0.75 if os.environ.get("ZQ_GEMM_3M", "1") != "0" else 1.0   # executed / canonical GEMM flops
 REF_SAMPLE_N = 1024          # 2n = 2048 reference run per step (~5-10 s on 16 cores)
+REF_FIT_ZQ = (500, 1024, 2048)   # sizes at which the reference is timed for the power-law fit
+REF_FIT_ZHEEV = (500, 1024)      # zheev(2n) at 2n = 4096 alone is ~5 min on 8 cores: left out of the bounded sample
+WORKLOAD = ("2n=%d quaternionic Hermitian eigendecomposition (values+vectors), G_sym seed 32 "
+            "[GPU arm: measured at this size; CPU reference arm: EXTRAPOLATED to this size from measured "
+            "2n<=4096 samples with a fitted power law a*n^p]")
+
+
+def bench_config(n2, nb):
+    """identical in both arms (the driver compares them)"""
+    return {"workload": WORKLOAD % n2, "n2": n2, "nb": nb or 64,
+            "l2": "inputs (16*n2*n B) larger than L2; fresh copy of the input every step"}
+
+
+def fit_power(ns, ts):
+    """least-squares a*n^p on log-log; returns (a, p)"""
+    import math
+    xs, ys = [math.log(x) for x in ns], [math.log(y) for y in ts]
+    k = len(xs)
+    if k < 2:
+        return (ts[0] / ns[0] ** 3, 3.0)
+    mx, my = sum(xs) / k, sum(ys) / k
+    p = sum((x - mx) * (y - my) for x, y in zip(xs, ys)) / sum((x - mx) ** 2 for x in xs)
+    return (math.exp(my - p * mx), p)
+
+
+def cpu_reference_points(ref, O, n_target, known=None):
+    """times ts::zquatev (reference, oracle/_ref) and LAPACK zheev(2n) (as test.cc:84-102 does) on the host cores at
+    the BASELINE.md 3 sizes, fits a*n^p to each, extrapolates to n_target.  `known`: {n: seconds} already measured."""
+    known = dict(known or {})
+    pts = []
+    for nn in REF_FIT_ZQ:
+        if nn > n_target:
+            continue
+        M = O.gen_testcc(nn)[2] if nn == 500 else O.gen_sym(nn, 32)      # n = 500: the test.cc matrix itself (config 1)
+        if nn in known:
+            tz = known[nn]
+        else:
+            t0 = time.perf_counter()
+            ref.zquatev(M)
+            tz = time.perf_counter() - t0
+        th = None
+        if nn in REF_FIT_ZHEEV:
+            t0 = time.perf_counter()
+            ref.zheev(M)
+            th = time.perf_counter() - t0
+        pts.append({"n": nn, "n2": 2 * nn, "zquatev_s": tz, "zheev_2n_s": th})
+    az, pz = fit_power([p["n"] for p in pts], [p["zquatev_s"] for p in pts])
+    hp = [p for p in pts if p["zheev_2n_s"] is not None]
+    ah, ph = fit_power([p["n"] for p in hp], [p["zheev_2n_s"] for p in hp]) if hp else (None, None)
+    return {"points": pts, "fit_zquatev": {"a": az, "p": pz}, "fit_zheev": {"a": ah, "p": ph},
+            "zquatev_extrapolated_s": az * n_target ** pz, "zheev_extrapolated_s": (ah * n_target ** ph) if ah else None}
 
 
 def parse():
@@ -100,14 +158,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def traffic_probe():
-    """dram bytes of ONE K1 launch from the committed ncu --set full capture (the step average over 16383 launches of
-    shrinking size is not capturable under ncu; `traffic` itself therefore stays null)"""
-    p = os.path.join(ROOT, "profiles", "r01_k1_traffic.json")
+def traffic_model(n, world):
+    """DRAM traffic of the K1 launches of one step, from the committed `ncu --set full` samples
+    (profiles/r02_k1_traffic.jsonl: one line per captured launch with its trailing size m, dram bytes read + written
+    and algorithmic bytes): the measured traffic/algorithmic ratio is interpolated in m and integrated over the
+    n - 1 launches of the step.  Returns (traffic_bytes_per_step, info) or (None, why)."""
+    p = os.path.join(ROOT, "profiles", "r02_k1_traffic.jsonl")
     try:
-        return json.load(open(p))
-    except Exception:
-        return None
+        rows = sorted((json.loads(l) for l in open(p) if l.strip()), key=lambda r: r["m"])
+        ms_ = [r["m"] for r in rows]
+        ratios = [(r["dram_read_bytes"] + r["dram_write_bytes"]) / r["algorithmic_bytes"] for r in rows]
+    except Exception as ex:
+        return None, "no ncu samples (%s)" % str(ex)[:80]
+    import bisect
+
+    def ratio(m):
+        i = bisect.bisect_left(ms_, m)
+        if i == 0:
+            return ratios[0]
+        if i >= len(ms_):
+            return ratios[-1]
+        f = (m - ms_[i - 1]) / (ms_[i] - ms_[i - 1])
+        return ratios[i - 1] + f * (ratios[i] - ratios[i - 1])
+
+    tot = 0.0
+    for k in range(n - 1):
+        m = n - k - 1
+        tot += (16.0 * m * m / world + 64.0 * m) * ratio(m)
+    return tot, {"source": "profiles/r02_k1_traffic.jsonl (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                 "sampled_m": ms_, "traffic_over_algorithmic": ratios}
 
 
 def measured_peaks():
@@ -137,7 +216,6 @@ def run_reference(args):
     ref.set_threads(cores)
     ns = min(REF_SAMPLE_N, n)
     M = O.gen_sym(ns, 32)
-    scale = (n / ns) ** 3
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -146,15 +224,18 @@ def run_reference(args):
         if it >= args.warmup:
             times.append(dt)
     per = sum(times) / len(times)
-    val = per * scale
-    sample = (f"reference ts::zquatev (oracle/_ref, OpenBLAS {cores} threads) at 2n={2 * ns}: {per:.3f} s/solve, "
-              f"scaled by (n/{ns})^3 = {scale:.0f} to 2n={args.n2}")
+    # once per run: the other sizes + zheev, power-law fit, extrapolation with the FITTED exponent
+    fit = cpu_reference_points(ref, O, n, known={ns: per})
+    p = fit["fit_zquatev"]["p"]
+    val = per * (n / ns) ** p
+    sample = (f"reference ts::zquatev (oracle/_ref, OpenBLAS {cores} threads) at 2n={2 * ns}: {per:.3f} s/solve measured per step; "
+              f"EXTRAPOLATED to 2n={args.n2} by (n/{ns})^p with p = {p:.3f} fitted over n = "
+              f"{[q['n'] for q in fit['points']]} (a cubic law would give {per * (n / ns) ** 3:.0f} s)")
     line = {"metric": METRIC % args.n2, "value": val, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"2n={args.n2} quaternionic Hermitian eigendecomposition (values+vectors)",
-                       "sample": sample},
-            "cpu_baseline": {"value": val, "unit": "s", "cores": cores, "kind": "reference", "sample": sample},
+            "config": bench_config(args.n2, args.nb), "extrapolated": True,
+            "cpu_baseline": {"value": val, "unit": "s", "cores": cores, "kind": "reference", "sample": sample, "fit": fit},
             "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "tflops_canonical": 164.0 / 3.0 * n ** 3 / val * 1e-12}
     print(json.dumps(line), flush=True)
@@ -246,9 +327,39 @@ def main():
     if world > 1:
         phases["gather"] = z.last_gather_ms()                    # NCCL gather of the eigenvector shards (inside "backtransform")
 
-    # ---- sanity of the last result (cheap, outside the timed region): sum(eig) = trace(A) ----
-    tr = torch.diagonal(left0[:, :n]).real.sum().item()
-    trace_err = abs(eig.sum().item() - tr)
+    # ---- parity of the LAST TIMED result at the full size, outside the timed region (checker: torch/cuBLAS) ----
+    # the checks the reference's own test prints (test.cc:104-112) in the north_star normalisation
+    from tests import gpu_util as GU
+    DE = GU.build_DE(left0)
+
+    def allsum(t):
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    quality = GU.device_quality(left0, work, eig, col_chunk=2048, rank=rank, world=world, reduce=allsum, DE=DE)
+    trace_err = quality["trace_err"]
+    normA = quality["eig_absmax"]                                 # ||A||_2 of the Hermitian matrix
+    if world > 1:
+        lst = [torch.zeros_like(eig) for _ in range(world)]
+        dist.all_gather(lst, eig)
+        quality["eig_identical_across_ranks"] = all(torch.equal(lst[0], t) for t in lst)
+        # run-to-run: a second collective solve must reproduce the first bit for bit (fixed-order sums, no atomics)
+        eig_first = eig.clone()
+        csum_first = work.view(torch.float64).sum().item()
+        step_device()
+        quality["bitwise_reproducible"] = bool(torch.equal(eig_first, eig)) and work.view(torch.float64).sum().item() == csum_first
+        # the same matrix through the single-GPU path on this rank (no collective): eigenvalues must agree
+        eig1 = torch.zeros_like(eig)
+        work[:n].copy_(left0)
+        info1 = z.zquatev_device(n2, work.data_ptr(), n2, eig1.data_ptr(), nb=args.nb, stream=stream, sync=True, dist=False)
+        quality["eig_vs_single_gpu_rel"] = (eig1 - eig_first).abs().max().item() / normA if info1 == 0 else None
+        barrier()
+        assert quality["eig_identical_across_ranks"], "ranks disagree on the eigenvalues"
+        assert quality["bitwise_reproducible"], "collective solve is not bit-reproducible run to run"
+        assert quality["eig_vs_single_gpu_rel"] is not None and quality["eig_vs_single_gpu_rel"] <= 1e-12, quality
+    quality["thresholds"] = "asserted: residual < 0.5, orthogonality < 1.5, pairing == 0, ascending, sumsq_relerr < 1e-12"
+    assert quality["pairing"] == 0.0 and quality["residual"] < 0.5 and quality["orthogonality"] < 1.5, quality
+    assert quality["ascending"] and quality["sumsq_relerr"] < 1e-12 and trace_err <= 1e-13 * n * normA, quality
 
     # ---- roofline of the dominant kernel (K1): one extra profiled step, per-launch CUDA events ----
     roof = None
@@ -265,9 +376,11 @@ def main():
         alg_bytes = sum(16.0 * (n - k - 1) ** 2 / world + 64.0 * (n - k - 1) for k in range(n - 1))
         peaks, src = measured_peaks()
         ach = alg_bytes / (k1_ms * 1e-3) * 1e-9 if k1_ms > 0 else None
+        traffic, traffic_info = traffic_model(n, world)
         roof = {"kernel": "k_matvec (K1 quaternion-Hermitian mat-vec, lower triangles)", "bound": "hbm",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": (ach / peaks["hbm_gbs"]) if ach else None,
-                "traffic": None, "traffic_probe": traffic_probe(), "peak_source": src, "launches": n - 1, "k1_ms_per_step": k1_ms,
+                "traffic": traffic, "traffic_info": traffic_info,
+                "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None, "peak_source": src, "launches": n - 1, "k1_ms_per_step": k1_ms,
                 "share_of_step": k1_ms / ph["device_total"] if ph["device_total"] else None,
                 "algorithmic_bytes_per_step": alg_bytes,
                 "note": "algorithmic bytes = 16 m^2 per column (lower triangles only; SURVEY 8d's full-storage figure is 32 m^2)"}
@@ -298,16 +411,30 @@ def main():
                 assert info == 0, info
                 if it >= 1:
                     opt_times.append(dt)
+            # the host result of the last e2e call: eigenvalues against the device-resident solve, and the residual of a
+            # spread sample of host columns (left AND right half) computed on the device
+            e2e_chk = {"eig_max_abs_diff_vs_device": float(np.max(np.abs(eig_h[:n] - eig.cpu().numpy())))}
+            if rank == 0:
+                cols = sorted(set(int(c) for c in np.linspace(0, n2 - 1, 16)))
+                Xs = torch.stack([host[c] for c in cols]).to(dev).T                  # 2n x 16
+                lam_s = torch.tensor([eig_h[c % n] for c in cols], dtype=torch.float64, device=dev)
+                Xa, Xb = Xs[:n], Xs[n:]
+                top = DE[0] @ Xa - (DE[1] @ Xb.conj()).conj()
+                bot = DE[1] @ Xa + (DE[0] @ Xb.conj()).conj()
+                rs = torch.sqrt(torch.linalg.norm(top - Xa * lam_s[None, :]) ** 2 + torch.linalg.norm(bot - Xb * lam_s[None, :]) ** 2).item()
+                e2e_chk["sample_cols"] = len(cols)
+                e2e_chk["sample_residual"] = rs / (len(cols) ** 0.5 * quality["fro_norm"] * 2.220446049250313e-16 * (n2 ** 0.5))
+                assert e2e_chk["sample_residual"] < 0.5 and e2e_chk["eig_max_abs_diff_vs_device"] <= 1e-12 * normA, e2e_chk
             te = torch.tensor([sum(opt_times) / len(opt_times)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e = {"value": te.item(), "unit": "s", "h2d_bytes_per_step": 16 * n2 * n, "d2h_bytes_per_step": 16 * n2 * n2 + 8 * n,
-                   "phases_ms": z.last_phases(),
+                   "phases_ms": z.last_phases(), "check": e2e_chk,
                    "note": "host-pointer C ABI call zquatev_b200_ex (== ts::zquatev), pinned host array" + ("; every rank uploads its copy of the input, rank 0 downloads all 2n columns, the others their own column blocks" if world > 1 else "")}
         except Exception as ex:   # e.g. not enough pinned host memory on the box
             e2e = {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the reference ----
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference ts::zquatev AND zheev(2n) at BASELINE.md 3's sizes ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
@@ -316,14 +443,15 @@ def main():
                 ref = O.RefLib()
                 cores = os.cpu_count() or 1
                 ref.set_threads(cores)
-                ns = min(REF_SAMPLE_N, n)
-                M = O.gen_sym(ns, 32)
-                t0 = time.perf_counter()
-                ref.zquatev(M)
-                dt = time.perf_counter() - t0
-                sc = (n / ns) ** 3
-                cpu = {"value": dt * sc, "unit": "s", "cores": cores, "kind": "reference",
-                       "sample": f"reference ts::zquatev (oracle/_ref) at 2n={2 * ns}: {dt:.3f} s measured on {cores} host threads, scaled by (n/{ns})^3={sc:.0f}"}
+                fit = cpu_reference_points(ref, O, n)
+                val = fit["zquatev_extrapolated_s"]
+                cpu = {"value": val, "unit": "s", "cores": cores, "kind": "reference", "extrapolated": True, "fit": fit,
+                       "sample": "reference ts::zquatev (oracle/_ref) measured on %d host threads at n = %s: %s s; zheev(2n) at n = %s: %s s; "
+                                 "EXTRAPOLATED to 2n=%d with the fitted law t = a*n^p, p = %.3f (zheev: p = %.3f -> %.0f s)" % (
+                                     cores, [q["n"] for q in fit["points"]], ["%.2f" % q["zquatev_s"] for q in fit["points"]],
+                                     [q["n"] for q in fit["points"] if q["zheev_2n_s"] is not None],
+                                     ["%.2f" % q["zheev_2n_s"] for q in fit["points"] if q["zheev_2n_s"] is not None],
+                                     n2, fit["fit_zquatev"]["p"], fit["fit_zheev"]["p"] or 0.0, fit["zheev_extrapolated_s"] or 0.0)}
         except Exception as ex:
             cpu = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": "failed: " + str(ex)[:120]}
 
@@ -332,11 +460,10 @@ def main():
         line = {"metric": METRIC % n2, "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"2n={n2} quaternionic Hermitian eigendecomposition (values+vectors), G_sym seed 32",
-                           "n2": n2, "nb": args.nb or 64, "l2": "inputs (16*n2*n B) larger than L2; fresh copy of the input every step",
-                           "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: reduction 1-D block-cyclic (64-column blocks), per-column reflector broadcast + partial mat-vec all-reduce by " + ("peer-memory stores fused into the panel kernels (CUDA IPC over NVLink)" if z.lib().zquatev_b200_dist_transport() == 2 else "NCCL collectives") + ", D&C replicated, back-transform sharded by eigenvector columns, NCCL gather of the result"},
+                "config": bench_config(n2, args.nb),
+                "setup": {"parallelism": "1 GPU" if world == 1 else f"{world} GPUs: reduction 1-D block-cyclic (64-column blocks), per-column reflector broadcast + partial mat-vec all-reduce by " + ("peer-memory stores fused into the panel kernels (CUDA IPC over NVLink)" if z.lib().zquatev_b200_dist_transport() == 2 else "NCCL collectives") + ", D&C replicated below the top merge, back-transform sharded by eigenvector columns, NCCL gather of the result"},
                 "tflops_canonical": 164.0 / 3.0 * n ** 3 / sec * 1e-12,
-                "phases_ms": phases, "trace_error": trace_err, "gpu_launches": launches, "clocks": clocks,
+                "phases_ms": phases, "trace_error": trace_err, "quality": quality, "gpu_launches": launches, "clocks": clocks,
                 "roofline": roof,
                 # second roofline (FP64 tensor path): executed GEMM flops of the back-transformation (32 n^3 / N per rank)
                 # over its CUDA-event time; peak = DMMA rate measured on this pool with tools/fp64_peak.cu

@@ -115,7 +115,7 @@ double zquatev_b200_last_trailing_ms(void);
  * (dist = 1) solve -- part of phase [3]; 0 for single-GPU solves.                                       */
 double zquatev_b200_last_gather_ms(void);
 
-/* Library build info, e.g. "zquatev_b200 0.1 sm_100a nb=32".                                   */
+/* Library build info, e.g. "zquatev_b200 0.2 sm_100a nb=64".                                   */
 const char* zquatev_b200_version(void);
 
 /* ---- kernel-level test doors (device pointers; used only by tests/ and bench.py) ------------ */
@@ -127,6 +127,9 @@ int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, vo
 int zq_test_zgemm(int ta, int tb, int M, int N, int K, const double* alpha, const void* A, long long lda,
                   const void* B, long long ldb, const double* beta, void* C, long long ldc, int lower, int reps,
                   double* ms);
+/* selects the complex-product scheme of the NEXT zq_test_zgemm calls: 1 = 3M (three real products, used by the
+ * solver for n >= 1024), 0 = conventional four products.  (A solve sets it again for itself.)              */
+void zq_test_set_gemm_3m(int on);
 /* K8: eigen-decomposition of the real symmetric tridiagonal (d, e): w[n] ascending, Z n x n (ld n). */
 int zq_test_stedc(int n, const double* d, const double* e, double* w, double* Z);
 /* K9: eigenvalues only by bisection.                                                             */

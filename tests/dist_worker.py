@@ -48,6 +48,40 @@ def main():
                 and r1 <= max(1.5 * r0, 0.6) and q1 <= max(1.5 * q0, 2.0) and same)
           out.append({"transport": transport, "n": n, "ok": bool(ok), "eig_dev": float(np.max(np.abs(e0 - e1)) / nrm), "res": r1, "res_single": r0,
                       "orth": q1, "orth_single": q0, "pair": p1, "ranks_agree": bool(same)})
+    # the paths that only exist at n >= 1024 (3M column-block trailing GEMM) and n >= 2048 (column-split top D&C
+    # merge; n % world == 0: in-place all-gather, else broadcast gather), against the golden eigenvalues of the
+    # unmodified reference and with the full residual / orthogonality / pairing check on the device
+    from tests import gpu_util as G
+    gpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sym_large.npz")
+    LARGE = dict(np.load(gpath)) if os.path.exists(gpath) else {}
+    os.environ["ZQ_DIST_NCCL"] = "0"
+    zd.init_from_torch()
+    for n, seed in [(1024, 34), (2048, 32), (2050, 33)]:
+        if f"eig_{n}_{seed}" not in LARGE:
+            continue
+        gold, meta = LARGE[f"eig_{n}_{seed}"], LARGE[f"meta_{n}_{seed}"]
+        M = O.gen_sym(n, seed)
+        left = torch.from_numpy(np.ascontiguousarray(M[:, :n].T)).cuda()
+        runs = []
+        for rep in range(2):
+            buf = torch.full((2 * n, 2 * n), float("nan"), dtype=torch.complex128, device="cuda")
+            buf[:n] = left
+            eig = torch.zeros(n, dtype=torch.float64, device="cuda")
+            info = z.zquatev_device(2 * n, buf.data_ptr(), 2 * n, eig.data_ptr(), nb=64, dist=True)
+            runs.append((info, eig, buf))
+        info, eig, buf = runs[0]
+        repro = bool(torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2].view(torch.float64), runs[1][2].view(torch.float64)))
+        q = G.device_quality(left, buf, eig, col_chunk=512, rank=rank, world=world,
+                             reduce=lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+        lst = [torch.zeros_like(eig) for _ in range(world)]
+        dist.all_gather(lst, eig)
+        same = all(torch.equal(lst[0], t) for t in lst)
+        dev_gold = float(np.max(np.abs(eig.cpu().numpy() - gold)) / meta[5])
+        ok = (info == 0 and same and repro and dev_gold <= 1e-12 and q["pairing"] == 0.0 and q["ascending"]
+              and q["residual"] <= meta[1] and q["orthogonality"] <= meta[2])
+        out.append({"transport": "peer", "n": n, "ok": bool(ok), "eig_dev_vs_reference": dev_gold, "res": q["residual"], "res_reference": float(meta[1]),
+                    "orth": q["orthogonality"], "orth_reference": float(meta[2]), "pair": q["pairing"], "ranks_agree": bool(same),
+                    "bitwise_reproducible": repro})
     zd.finalize()
     if rank == 0:
         print("DIST_RESULT " + json.dumps(out), flush=True)

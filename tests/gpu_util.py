@@ -1,5 +1,6 @@
 """helpers for the -m gpu tests: torch is only the device-memory / stream plumbing."""
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -102,3 +103,80 @@ def solve_host(M, jobz=1, nb=0, ld2=None):
     eig = np.full(n2, -777.0)
     info = z.zquatev(n2, buf, ld2, eig, jobz=jobz, nb=nb)
     return eig, buf[:n2, :], info
+
+
+# ------------------------------------------------------------------------------------------------
+# north_star quality metrics at sizes where the CPU oracle's O(N^3) numpy products are too slow:
+# the SAME formulas as oracle.zquatev_oracle.quality (which restates test.cc:104-112), evaluated on the
+# device with torch (cuBLAS zgemm) -- checker only, never on the product path.
+# ------------------------------------------------------------------------------------------------
+def build_DE(left0):
+    """(D, E) as full n x n (row, col) tensors from the lower triangles of the column-major left half [n][2n]:
+    M = [[D, -conj E], [E, conj D]], D Hermitian with real diagonal, E antisymmetric (zquatev.h:40-44)."""
+    n = left0.shape[0]
+    Dl = left0[:, :n].T                                   # (row, col) view; lower triangle valid
+    El = left0[:, n:].T
+    D = torch.tril(Dl, -1)
+    D = D + D.conj().T
+    D.diagonal().copy_(torch.diagonal(Dl).real.to(torch.complex128))
+    E = torch.tril(El, -1)
+    E = E - E.T
+    return D, E
+
+
+def device_quality(left0, out, eig, col_chunk=2048, rank=0, world=1, reduce=None, DE=None):
+    """left0 : [n][2n] complex128 device tensor = column-major INPUT left half (A; B); only its lower
+               triangles are meaningful (what the solver reads).
+       out   : [2n][2n] complex128 device tensor = column-major RESULT (all 2n columns).
+       eig   : [n] float64 device tensor.
+    With world > 1 every rank checks the column chunks c = rank, rank + world, ... of ITS OWN copy of the
+    gathered result and `reduce(t)` (a SUM all-reduce of a float64 tensor) combines the squared norms, so the
+    numbers cover all 2n columns on every N and also see a wrong gather.
+    Returns dict(residual, orthogonality, pairing, trace_err, sumsq_relerr, ascending, fro_norm):
+       residual      = ||M V - V L||_F / (N ||M||_F eps),   orthogonality = ||V^H V - I||_F / (N eps)   (N = 2n)
+       pairing       = max |right half - Theta(left half)|  (must be exactly 0)."""
+    n = left0.shape[0]
+    N = 2 * n
+    eps = 2.220446049250313e-16
+    dev_ = left0.device
+    D, E = DE if DE is not None else build_DE(left0)
+    Dl = left0[:, :n].T
+    fro2 = 2.0 * (torch.linalg.norm(D) ** 2 + torch.linalg.norm(E) ** 2)
+    lam = torch.cat([eig, eig])
+    r2 = torch.zeros((), dtype=torch.float64, device=dev_)
+    o2 = torch.zeros((), dtype=torch.float64, device=dev_)
+    chunks = list(range(0, N, col_chunk))
+    for ci, c0 in enumerate(chunks):
+        if ci % world != rank:
+            continue
+        c1 = min(N, c0 + col_chunk)
+        X = out[c0:c1].T                                  # N x nc, columns contiguous in memory
+        Xa, Xb = X[:n], X[n:]
+        # M X = [D Xa - conj(E) Xb ; E Xa + conj(D) Xb],  conj(E) Xb = conj(E conj(Xb))
+        top = D @ Xa - (E @ Xb.conj()).conj()
+        bot = E @ Xa + (D @ Xb.conj()).conj()            # conj(D) Xb = conj(D conj(Xb))
+        l = lam[c0:c1][None, :]
+        r2 += torch.linalg.norm(top - Xa * l) ** 2 + torch.linalg.norm(bot - Xb * l) ** 2
+        del top, bot
+        G = out @ X.conj()                                # conj of the N x nc block of V^H V (out as a matrix is V^T); no 2n x 2n temporary
+        idx = torch.arange(c0, c1, device=dev_)
+        G[idx, idx - c0] -= 1.0
+        o2 += torch.linalg.norm(G) ** 2
+        del G
+    if reduce is not None:
+        t = torch.stack([r2, o2])
+        reduce(t)
+        r2, o2 = t[0], t[1]
+    # pairing: columns n + c = Theta(column c) = (-conj V_c ; conj U_c), exact
+    pair = 0.0
+    for c0 in range(0, n, col_chunk):
+        c1 = min(n, c0 + col_chunk)
+        L, R = out[c0:c1], out[n + c0:n + c1]             # [col][row]
+        pair = max(pair, (R[:, :n] + L[:, n:].conj()).abs().max().item(), (R[:, n:] - L[:, :n].conj()).abs().max().item())
+    fro = math.sqrt(fro2.item())
+    tr = torch.diagonal(Dl).real.sum().item()
+    return {"residual": math.sqrt(r2.item()) / (N * fro * eps), "orthogonality": math.sqrt(o2.item()) / (N * eps),
+            "pairing": pair, "trace_err": abs(eig.sum().item() - tr),
+            "sumsq_relerr": abs((eig ** 2).sum().item() - 0.5 * fro2.item()) / (0.5 * fro2.item()),   # ||M||_F^2 = 2 sum(lambda^2)
+            "ascending": bool(torch.all(eig[1:] >= eig[:-1]).item()) if n > 1 else True, "fro_norm": fro,
+            "eig_absmax": eig.abs().max().item()}

@@ -46,8 +46,12 @@ def test_k1_ignores_upper_triangles():
 @pytest.mark.parametrize("ta,tb,M,N,Kd,lower", [(0, 1, 100, 100, 128, 1), (0, 1, 67, 67, 40, 1), (1, 0, 64, 130, 300, 0),
                                                 (0, 0, 200, 77, 64, 0), (0, 0, 5, 3, 2, 0), (1, 1, 33, 65, 17, 0),
                                                 (0, 1, 129, 129, 256, 0)])
-def test_zgemm(ta, tb, M, N, Kd, lower):
+@pytest.mark.parametrize("three_m", [0, 1], ids=["4-product", "3M"])
+def test_zgemm(ta, tb, M, N, Kd, lower, three_m):
+    """both complex-product schemes, selected explicitly (the solver picks 3M for n >= 1024)"""
     from tests import gpu_util as G
+    from zquatev_b200 import api
+    api.lib().zq_test_set_gemm_3m(three_m)
     rng = np.random.default_rng(M * 7 + N)
     cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
     A = cr(Kd, M) if ta else cr(M, Kd)

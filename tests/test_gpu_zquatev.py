@@ -15,6 +15,10 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TESTCC = json.load(open(os.path.join(GOLD, "testcc_eigs.json")))
 SYM = json.load(open(os.path.join(GOLD, "sym_eigs.json")))
 
+# large cases: eigenvalues + quality numbers of the unmodified reference (tests/golden/make_golden_large.py)
+_LARGE_PATH = os.path.join(GOLD, "sym_large.npz")
+LARGE = dict(np.load(_LARGE_PATH)) if os.path.exists(_LARGE_PATH) else {}
+
 # north_star tolerance: eigenvalues within 1e-12 * ||A|| (2-norm of the matrix)
 EIG_TOL = 1e-12
 
@@ -25,13 +29,16 @@ def check_quality(M, out, eig, g=None):
     if g is None:
         assert res < 1.0 and orth < 2.0
     else:
-        # "at or below the reference's": both numbers are in units of N*eps, so for tiny matrices they
-        # are a handful of roundings and move by O(1) with the BLAS build / summation order; the
-        # comparison therefore carries 15 % slack and, for n <= 64 ONLY, the floors 0.6 (residual) /
-        # 2.0 (orthogonality); for n > 64 there is no floor (at n = 200, 500 the reference has 0.048 / 1.02 and 0.027 / 0.92).
-        small = len(eig) <= 64
-        assert res <= max(1.15 * g["residual"], 0.6 if small else 0.0), (res, g["residual"])
-        assert orth <= max(1.15 * g["orthogonality"], 2.0 if small else 0.0), (orth, g["orthogonality"])
+        # "at or below the reference's" (north_star).  Both numbers are in units of N*eps; for n >= 200 the comparison is
+        # strict (<= 1.0 x the reference's value from the golden file: at n = 200, 500 the reference has 0.048 / 1.02 and
+        # 0.027 / 0.92, this solver 0.03 / 0.6 and 0.014 / 0.55).  For tiny matrices the numbers are a handful of
+        # roundings and move by O(1) with the BLAS build / summation order: 15 % slack for n < 200 and, for n <= 64
+        # ONLY, the floors 0.6 (residual) / 2.0 (orthogonality).
+        nn = len(eig)
+        slack = 1.0 if nn >= 200 else 1.15
+        small = nn <= 64
+        assert res <= max(slack * g["residual"], 0.6 if small else 0.0), (res, g["residual"])
+        assert orth <= max(slack * g["orthogonality"], 2.0 if small else 0.0), (orth, g["orthogonality"])
     return res, orth
 
 
@@ -89,7 +96,8 @@ def test_against_reference_library(n, seed, reduction_path):
     rr, orr, _ = O.quality(M, outr, er)
     res, orth, pair = O.quality(M, out, eig[:n])
     fl = (0.6, 2.0) if n < 64 else (0.0, 0.0)
-    assert pair == 0.0 and res <= max(1.15 * rr, fl[0]) and orth <= max(1.15 * orr, fl[1]), (res, rr, orth, orr)
+    slack = 1.0 if n >= 200 else 1.15
+    assert pair == 0.0 and res <= max(slack * rr, fl[0]) and orth <= max(slack * orr, fl[1]), (res, rr, orth, orr)
     gaps = np.minimum(np.diff(er, prepend=-np.inf), np.diff(er, append=np.inf))
     for i in range(n):
         if gaps[i] < 1e-6 * nrm:
@@ -269,6 +277,38 @@ def test_properties_at_scale_device_resident(n):
     U, W = V[:n, :n], V[n:, :n]
     assert torch.equal(V[:n, n:], -W.conj()) and torch.equal(V[n:, n:], U.conj())
     assert bool(torch.all(eig[1:] >= eig[:-1]))
+
+
+@pytest.mark.parametrize("n,seed,path", [(1024, 34, "host"), (2048, 32, "device"), (2050, 33, "host"), (4096, 32, "device"), (4096, 32, "host")])
+def test_large_golden_vs_reference(n, seed, path):
+    """BASELINE config 2 (2n = 8192, G_sym(4096, 32)) and the sizes below it AT THEIR SIZE against the unmodified
+    reference: eigenvalues within 1e-12 ||A||, residual and orthogonality at or below the reference's own numbers
+    (golden file, generated by tests/golden/make_golden_large.py), exact pairing.  `host` goes through the
+    reference-facing host-pointer entry (== ts::zquatev), `device` through the device-resident one."""
+    import torch
+    import zquatev_b200 as z
+    from tests import gpu_util as G
+    key = f"{n}_{seed}"
+    if "eig_" + key not in LARGE:
+        pytest.skip("golden file lacks this case")
+    gold, meta = LARGE["eig_" + key], LARGE["meta_" + key]      # meta: info, res, orth, pair, fro, two_norm, seconds
+    M = O.gen_sym(n, seed)
+    left = torch.from_numpy(np.ascontiguousarray(M[:, :n].T)).cuda()          # [n][2n] column-major left half
+    eig = torch.zeros(n, dtype=torch.float64, device="cuda")
+    if path == "device":
+        buf = torch.full((2 * n, 2 * n), float("nan"), dtype=torch.complex128, device="cuda")
+        buf[:n] = left
+        info = z.zquatev_device(2 * n, buf.data_ptr(), 2 * n, eig.data_ptr())
+    else:
+        e_h, out_h, info = G.solve_host(M)
+        eig.copy_(torch.from_numpy(e_h[:n]))
+        buf = torch.from_numpy(np.ascontiguousarray(out_h.T)).cuda()
+    assert info == 0
+    assert np.max(np.abs(eig.cpu().numpy() - gold)) <= EIG_TOL * meta[5]
+    q = G.device_quality(left, buf, eig, col_chunk=1024)
+    assert q["pairing"] == 0.0 and q["ascending"]
+    assert q["residual"] <= meta[1] and q["orthogonality"] <= meta[2], (q, meta[1], meta[2])
+    assert q["sumsq_relerr"] < 1e-13 and q["trace_err"] <= 1e-13 * n * meta[5]
 
 
 @pytest.mark.skipif(os.environ.get("ZQ_TEST_EXPERIMENTAL", "0") == "0",

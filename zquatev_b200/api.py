@@ -37,6 +37,7 @@ SYMBOLS = {
     "zquatev_b200_version": (ctypes.c_char_p, []),
     "zq_test_matvec": (_I, [_I, _I, _P, _LL, _P, _P, _I, _P]),
     "zq_test_zgemm": (_I, [_I, _I, _I, _I, _I, _P, _P, _LL, _P, _LL, _P, _P, _LL, _I, _I, _P]),
+    "zq_test_set_gemm_3m": (None, [_I]),
     "zq_test_stedc": (_I, [_I, _P, _P, _P, _P]),
     "zq_test_bisect": (_I, [_I, _P, _P, _P]),
     "zq_test_tridiag": (_I, [_I, _I, _P, _LL, _P, _P, _P, _P]),

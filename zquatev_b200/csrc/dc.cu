@@ -508,10 +508,9 @@ void dc_destroy(DcWs* ws) {
 int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, double** Zres, int** perm, int* info,
              cudaStream_t st, const DcDist* dd) {
   const size_t ld = (size_t)n;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_this_device(attr_done)) {
     cudaFuncSetAttribute(k_dc_gemm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DG_ST * DG_STAGE * sizeof(double)));
-    attr_done = true;
   }
   k_dc_init<<<1, 1024, 0, st>>>(n, d, e, ws->d, ws->e, ws->scale);
   if (ws->nbounds > 0) k_dc_tear<<<cdiv(ws->nbounds, 128), 128, 0, st>>>(ws->nbounds, ws->bounds, ws->d, ws->e);

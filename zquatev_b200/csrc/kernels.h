@@ -1,6 +1,7 @@
 // Host-callable launchers of the zquatev B200 kernels (all asynchronous on `st`).
 // Kernel ids K1..K10 follow SURVEY.md 7.2 / DESIGN.md.
 #pragma once
+#include <atomic>
 #include "common.cuh"
 
 namespace zq {
@@ -21,6 +22,14 @@ __host__ __device__ inline int dot_chunk_rows(int rows) {
 constexpr int ROWS_PER_CTA = 256;
 constexpr int PANEL_ROWS = 32;      // rows per CTA of the latency-bound panel kernels
 constexpr int MAX_NB_PANEL = 64;    // largest panel width
+
+// cudaFuncSetAttribute applies to the CURRENT device only, so the "already done" flags are per device
+inline bool first_use_on_this_device(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return !(mask.fetch_or(bit) & bit);
+}
 
 // launch of a kernel of the per-column chain: with ZQ_PDL != 0 (default) the launch carries the programmatic-stream-
 // serialization attribute, see pdl_enter() in common.cuh

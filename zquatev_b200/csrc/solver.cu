@@ -48,6 +48,8 @@ struct Plan {
   double* eig_dev = nullptr;
   cudaEvent_t ev[6] = {};
   cudaEvent_t ev_gather = nullptr;   // multi-GPU: recorded before the NCCL gather of the eigenvector shards
+  cudaEvent_t done = nullptr;        // recorded at the end of every solve: the next user of this workspace waits on it,
+  bool done_valid = false;           // so an asynchronous solve on another stream cannot race with it
   double gather_ms = 0;
   std::vector<cudaEvent_t> k1ev;
   std::vector<cudaEvent_t> k4ev;   // profiling: event pair around every trailing-update GEMM
@@ -110,6 +112,7 @@ static void plan_free(Plan* p) {
   if (p->dc) dc_destroy(p->dc);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->ev_gather) cudaEventDestroy(p->ev_gather);
+  if (p->done) cudaEventDestroy(p->done);
   for (auto& e : p->k1ev) cudaEventDestroy(e);
   for (auto& e : p->k4ev) cudaEventDestroy(e);
   delete p;
@@ -167,6 +170,7 @@ static int plan_create(int n, int nb, Plan** out) {
   p->info_dev = (int*)(b + o_info); p->eig_dev = (double*)(b + o_eig);
   for (auto& ev : p->ev) cudaEventCreate(&ev);
   cudaEventCreate(&p->ev_gather);
+  cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming);
   *out = p;
   return 0;
 }
@@ -355,6 +359,10 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   }
   w.rank = g_rank;
   w.world = G;
+  struct Restore {              // the cached plan must never keep the distributed geometry, whatever the exit path
+    PanelWs& w;
+    ~Restore() { w.rank = 0; w.world = 1; }
+  } restore{w};
   const bool use_px = g_px.world == G && (size_t)n <= g_px.nmax;
   if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
   PeerX px = g_px;
@@ -411,8 +419,6 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   p->launches += 1;
   if (use_px) g_seq_base += (unsigned long long)n + 8ull;
   if (n >= 2048) l2_window(st, w.pan, 0);
-  w.rank = 0;
-  w.world = 1;
   return 0;
 }
 
@@ -539,6 +545,8 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   PanelWs& w = p->pw;
   w.A = Dfull;
   w.lda = ld;
+  w.rank = 0;
+  w.world = 1;
   p->launches = 0;
   p->gather_ms = -1.0;
   zgemm_allow_3m(n >= 1024);
@@ -593,15 +601,18 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
         ZQ_NCCL_CHECK(g_nccl.AllGather(R + (size_t)g_rank * per * ld, R, cnt, ncclDouble, g_comm, st));
       } else {
         ZQ_NCCL_CHECK(g_nccl.GroupStart());
-        for (int r = 0; r < g_world; ++r) {
+        ncclResult_t bad = ncclSuccess;         // an error inside the group must not leave it open
+        for (int r = 0; r < g_world && bad == ncclSuccess; ++r) {
           const int c0 = r * per < n ? r * per : n, nc = (c0 + per <= n) ? per : n - c0;
           if (nc <= 0) continue;
           cplx* L = Dfull + (size_t)c0 * ld;
           cplx* R = Dfull + (size_t)(n + c0) * ld;
-          ZQ_NCCL_CHECK(g_nccl.Broadcast(L, L, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
-          ZQ_NCCL_CHECK(g_nccl.Broadcast(R, R, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st));
+          bad = g_nccl.Broadcast(L, L, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st);
+          if (bad == ncclSuccess) bad = g_nccl.Broadcast(R, R, (size_t)2 * nc * ld, ncclDouble, r, g_comm, st);
         }
-        ZQ_NCCL_CHECK(g_nccl.GroupEnd());
+        const ncclResult_t endr = g_nccl.GroupEnd();
+        ZQ_NCCL_CHECK(bad);
+        ZQ_NCCL_CHECK(endr);
       }
     }
     if (p->timing) cudaEventRecord(p->ev[4], st);
@@ -668,6 +679,12 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   Plan* p = nullptr;
   rc = get_plan(n, nb, &p);
   if (rc) return rc;
+  // the workspace may still be in use by an asynchronous solve enqueued on ANOTHER stream: order after it
+  if (p->done_valid) ZQ_CUDA_CHECK(cudaStreamWaitEvent(st, p->done, 0));
+  struct DoneMark {             // every exit path (errors included) leaves the completion event behind the enqueued work
+    Plan* p; cudaStream_t st;
+    ~DoneMark() { if (cudaEventRecord(p->done, st) == cudaSuccess) p->done_valid = true; else cudaGetLastError(); }
+  } done_mark{p, st};
   if (devp) {
     rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, opt ? opt->dist : 0, 1, st);
     if (rc) return rc;
@@ -742,7 +759,7 @@ struct Lane {
   bool graph_failed = false;
 };
 std::vector<Lane> g_lanes;
-int g_lanes_n = -1;
+int g_lanes_n = -1, g_lanes_dev = -1;
 bool g_lanes_small = false;     // reduction baked into the lanes' graphs: K5 (true) or the K1-K4 chain
 int g_batch_graph_launches = 0, g_batch_eager_solves = 0;
 
@@ -758,6 +775,7 @@ void lanes_free() {
   }
   g_lanes.clear();
   g_lanes_n = -1;
+  g_lanes_dev = -1;
 }
 
 // H2D of the left half, full solve, D2H of the result / eigenvalues / status: everything a lane does for one problem
@@ -822,23 +840,32 @@ int zquatev_b200_batched(int batch, int n2, void* D, int ld2, long long strideD,
   int dev = 0;
   ZQ_CUDA_CHECK(cudaGetDevice(&dev));
   const bool small_now = n <= small_n_max();
-  if (g_lanes_n != n || (int)lanes.size() < nl || g_lanes_small != small_now) {   // (graphs bake the reduction in)
+  if (g_lanes_n != n || (int)lanes.size() < nl || g_lanes_small != small_now || g_lanes_dev != dev) {   // (graphs bake the reduction in)
     lanes_free();
-    lanes.assign(nl, Lane());
+    // build into a local vector and commit only when every lane is complete: a failure half-way (e.g. pinned host
+    // memory exhausted) must not leave half-built lanes cached for the next call
+    std::vector<Lane> fresh(nl);
+    auto build = [&]() -> int {
+      for (auto& L : fresh) {
+        int r = plan_create(n, DEFAULT_NB, &L.p);
+        if (r) return r;
+        ZQ_CUDA_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+        ZQ_CUDA_CHECK(cudaMalloc(&L.p->Dfull, (size_t)n2 * n2 * sizeof(cplx)));
+        L.p->dc = dc_create(n);                  // not inside a capture later
+        if (!L.p->dc) return zq_cuda_fail(cudaGetLastError(), __FILE__, __LINE__);
+        ZQ_CUDA_CHECK(cudaMallocHost(&L.hinfo, sizeof(int) * 4));
+        // pinned staging: a D2H copy into pageable memory would block the host and serialise the lanes
+        ZQ_CUDA_CHECK(cudaMallocHost(&L.hbuf, (size_t)n2 * n2 * sizeof(cplx)));
+        ZQ_CUDA_CHECK(cudaMallocHost(&L.heig, (size_t)n * sizeof(double)));
+      }
+      return 0;
+    };
+    rc = build();
+    lanes.swap(fresh);                           // lanes_free() releases whatever was built
+    if (rc) { lanes_free(); return rc; }
     g_lanes_n = n;
     g_lanes_small = small_now;
-    for (auto& L : lanes) {
-      rc = plan_create(n, DEFAULT_NB, &L.p);
-      if (rc) return rc;
-      ZQ_CUDA_CHECK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
-      ZQ_CUDA_CHECK(cudaMalloc(&L.p->Dfull, (size_t)n2 * n2 * sizeof(cplx)));
-      L.p->dc = dc_create(n);                  // not inside a capture later
-      if (!L.p->dc) return zq_cuda_fail(cudaGetLastError(), __FILE__, __LINE__);
-      ZQ_CUDA_CHECK(cudaMallocHost(&L.hinfo, sizeof(int) * 4));
-      // pinned staging: a D2H copy into pageable memory would block the host and serialise the lanes
-      ZQ_CUDA_CHECK(cudaMallocHost(&L.hbuf, (size_t)n2 * n2 * sizeof(cplx)));
-      ZQ_CUDA_CHECK(cudaMallocHost(&L.heig, (size_t)n * sizeof(double)));
-    }
+    g_lanes_dev = dev;
   }
   std::atomic<int> next(0), worst(0), fail(0), graph_launches(0), eager_solves(0);
   // pinned staging -> caller's arrays, after the lane's stream has drained
@@ -993,7 +1020,7 @@ double zquatev_b200_last_trailing_ms(void) {
   return g_plan ? g_plan->k4_ms : 0.0;
 }
 
-const char* zquatev_b200_version(void) { return "zquatev_b200 0.1 sm_100a nb=64"; }
+const char* zquatev_b200_version(void) { return "zquatev_b200 0.2 sm_100a nb=64"; }
 
 // ---- test doors ------------------------------------------------------------------------------
 int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, void* y, int reps, double* ms) {
@@ -1045,6 +1072,8 @@ int zq_test_zgemm(int ta, int tb, int M, int N, int K, const double* alpha, cons
   ZQ_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
+
+void zq_test_set_gemm_3m(int on) { zgemm_allow_3m(on); }
 
 int zq_test_stedc(int n, const double* d, const double* e, double* w, double* Z) {
   cudaStream_t st = 0;

@@ -372,10 +372,9 @@ void launch_3m(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const
   using TileA = OpTile<64, TA == 1, BK>;
   using TileB = OpTile<32, TB == 0, BK>;
   const size_t smem = (size_t)STAGES * (TileA::ELEMS + TileB::ELEMS) * sizeof(cplx);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_this_device(attr_done)) {
     cudaFuncSetAttribute(k_zgemm_3m<BK, STAGES, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
   }
   dim3 g((M + 63) / 64, ncb >= 0 ? 2 * ncb : 2 * ((N + 63) / 64), batch);
   if (g.y == 0) return;
@@ -390,10 +389,9 @@ void launch_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, cons
   using TileB = OpTile<BN, TB == 0, BK>;
   constexpr int NTHREADS = (BM / 32) * (BN / 32) * 32;
   const size_t smem = (size_t)STAGES * (TileA::ELEMS + TileB::ELEMS) * sizeof(cplx);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_this_device(attr_done)) {
     cudaFuncSetAttribute(k_zgemm_mma<BM, BN, BK, STAGES, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
   }
   dim3 g((M + BM - 1) / BM, ncb >= 0 ? ncb : (N + BN - 1) / BN, batch);
   if (g.y == 0) return;
