@@ -367,7 +367,7 @@ def main():
     step_device()
     torch.cuda.synchronize()
     ph = z.last_phases()
-    k4_ms = z.last_trailing_ms() if world == 1 else 0.0
+    k4_ms = z.last_trailing_ms()                                  # event pair around every trailing-update GEMM (any N)
     z.set_profiling(False)
     barrier()
     if rank == 0:
@@ -477,7 +477,7 @@ def main():
                                   "peak_source": "own measurement (profiles/r01_fp64_peak.jsonl: DMMA 37.1, DFMA 36.9 TFLOP/s); MEASURED_PEAKS.json has no FP64 entry",
                                   "note": "phase time includes operand staging, T factors, pairing and (N > 1) the NCCL gather"},
                 "cpu_baseline": cpu, "e2e": e2e}
-        if world == 1 and k4_ms > 0:
+        if k4_ms > 0:
             # third roofline: the trailing rank-2k update [D;E] -= L R^H (K4), event pair around each of its n/nb launches in
             # the profiled step.  canonical flops = 32 m^2 kb per panel (lower triangles of D and E, K = 4 kb complex)
             nbb = args.nb or 64
@@ -490,8 +490,9 @@ def main():
             ex = GEMM_EXEC if n >= 1024 else 1.0
             line["roofline_fp64_trailing"] = {
                 "kernel": "k_zgemm_3m<0,1> lower (K4 trailing rank-2k update, DMMA m8n8k4)", "bound": "tensor",
-                "achieved": ex * f4 / (k4_ms * 1e-3) * 1e-12, "peak": 37.1, "unit": "TFLOP/s",
-                "frac": ex * f4 / (k4_ms * 1e-3) * 1e-12 / 37.1, "canonical_tflops": f4 / (k4_ms * 1e-3) * 1e-12,
+                "achieved": ex * f4 / world / (k4_ms * 1e-3) * 1e-12, "peak": 37.1, "unit": "TFLOP/s",
+                "frac": ex * f4 / world / (k4_ms * 1e-3) * 1e-12 / 37.1, "canonical_tflops": f4 / world / (k4_ms * 1e-3) * 1e-12,
+                "note": "per rank: each rank updates the 64-column blocks it owns (1/N of the flops)",
                 "k4_ms_per_step": k4_ms, "share_of_step": k4_ms / ph["device_total"] if ph["device_total"] else None,
                 "launches": (n - 1 + nbb - 1) // nbb,
                 "peak_source": "own measurement (profiles/r01_fp64_peak.jsonl)"}

@@ -50,7 +50,10 @@ typedef struct zq_options {
                         zquatev.cc:64)                                                          */
   void* stream;      /* cudaStream_t to run on (NULL = the legacy default stream)               */
   int sync;          /* device_ptrs only: 1 = wait for completion and return info (default when
-                        the struct is zero-initialised is 0 = asynchronous, info not checked)   */
+                        the struct is zero-initialised is 0 = asynchronous, info not checked).  An
+                        asynchronous solve keeps using the handle's plan of this size after the call
+                        returns; the next solve that needs the same plan is ordered behind it on the
+                        device (event wait), whatever stream it uses.                            */
   int col0, ncols;   /* eigenvector column block [col0, col0+ncols) to back-transform and return
                         (ncols = 0: all n).  Multi-GPU runs shard the back-transformation by
                         eigenvector columns: columns outside the block (and their
@@ -68,6 +71,30 @@ typedef struct zq_options {
 
 /* Same contract as zquatev_b200 plus options.  With jobz = 0 D is destroyed (holds reflectors). */
 int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt);
+
+/* ---- handles -----------------------------------------------------------------
+ * The reference allocates and frees its workspace inside every call (zquatev.cc:63-66, marked TODO).  A handle
+ * owns a cache of plans -- the device workspace of one (n2, nb) -- on the device that was current when it was
+ * created, and its own lock:
+ *   - several sizes stay warm side by side (up to 4; the least recently used is dropped first, also when the
+ *     device runs out of memory), so a caller alternating between sizes never re-allocates;
+ *   - solves through different handles do not serialise on each other (no process-wide lock); two solves through
+ *     the SAME handle are serialised on the host and, when they use different streams, ordered on the device by
+ *     an event recorded at the end of every solve;
+ *   - zquatev_b200 / zquatev_b200_ex / ts::zquatev use a default handle per device.
+ * zquatev_b200_solve has the contract of zquatev_b200_ex.  Returns -7 when the current device is not the
+ * handle's.  Collective (dist = 1) solves share the process's one communicator and are serialised.            */
+typedef struct zq_handle_s* zq_handle_t;
+int zquatev_b200_create(zq_handle_t* handle);
+int zquatev_b200_destroy(zq_handle_t handle);
+int zquatev_b200_solve(zq_handle_t handle, int n2, void* D, int ld2, double* eig, const zq_options* opt);
+/* Allocates everything a solve of this size with these options needs, now (handle NULL = default handle).   */
+int zquatev_b200_reserve(zq_handle_t handle, int n2, const zq_options* opt);
+/* Workspace query: device bytes such a plan holds (panels, partial sums, GEMM operands; + tridiagonal D&C when
+ * jobz = 1; + the 2n x 2n staging array when D is a host pointer).  Allocates nothing.                       */
+int zquatev_b200_workspace_query(int n2, const zq_options* opt, unsigned long long* device_bytes);
+/* phase timings of the handle's last solve (layout of zquatev_b200_last_phases)                              */
+int zquatev_b200_handle_phases(zq_handle_t handle, double ms[8]);
 
 /* `batch` independent problems of the same size (BASELINE config 5): problem b uses
  * D + b*strideD (complex elements) and eig + b*strideEig; info[b] receives its return code.
@@ -97,11 +124,10 @@ void zquatev_b200_dist_finalize(void);
  * final gather).  Transport 2 is chosen when every peer can be mapped; ZQ_DIST_NCCL=1 forces 1.       */
 int zquatev_b200_dist_transport(void);
 
-/* Workspace cache: plans (device workspaces for one n) are created on first use and cached per
- * thread-safe global table; this frees them.                                                  */
+/* Frees the plans of the default handles (all devices) and the lanes of the batched entry.      */
 void zquatev_b200_release(void);
 
-/* Milliseconds of the phases of the LAST call on this thread's plan, measured with CUDA events
+/* Milliseconds of the phases of the LAST call through the default handle of the current device, measured with CUDA events
  * on the solver's stream: [0] H2D, [1] tridiagonalisation, [2] tridiagonal eigensolver,
  * [3] back-transformation + pairing, [4] D2H, [5] total device time, [6] K1 mat-vec launches
  * (only when profiling is on), [7] number of kernel launches.  Returns 0 when no plan exists.  */

@@ -23,6 +23,12 @@ _P, _I, _LL, _D = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_dou
 SYMBOLS = {
     "zquatev_b200": (_I, [_I, _P, _I, _P]),
     "zquatev_b200_ex": (_I, [_I, _P, _I, _P, ctypes.POINTER(ZqOptions)]),
+    "zquatev_b200_create": (_I, [ctypes.POINTER(_P)]),
+    "zquatev_b200_destroy": (_I, [_P]),
+    "zquatev_b200_solve": (_I, [_P, _I, _P, _I, _P, ctypes.POINTER(ZqOptions)]),
+    "zquatev_b200_reserve": (_I, [_P, _I, ctypes.POINTER(ZqOptions)]),
+    "zquatev_b200_workspace_query": (_I, [_I, ctypes.POINTER(ZqOptions), ctypes.POINTER(ctypes.c_ulonglong)]),
+    "zquatev_b200_handle_phases": (_I, [_P, _P]),
     "zquatev_b200_batched": (_I, [_I, _I, _P, _I, _LL, _P, _LL, _P]),
     "zquatev_b200_batched_stats": (None, [_P, _P]),
     "zquatev_b200_release": (None, []),

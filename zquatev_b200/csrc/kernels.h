@@ -54,8 +54,11 @@ struct PanelWs {
   size_t lda;         // leading dimension of A (complex elements)
   cplx* A;            // 2n x n: D rows [0,n), E rows [n,2n)
   cplx* pan;          // [4][nb][n]: Va, Vb, Wa, Wb
-  quat* x;            // [n] current (updated) column
-  quat* vq;           // [n] current reflector, zero outside its support
+  quat* x;            // [xrec + 3] current (updated) column k in rows [k+1, n), followed at x[xrec] by the scalar
+                      //   record of the column: (d_k, e_k = ||x||, tau_k, 0), alpha_k, u1^{-1}.  The reflector is
+                      //   v[r] = x[r] u1^{-1} (v[k+1] = 1): every consumer forms it on the fly.
+  int xrec;           // index of the record (n on one GPU; the capacity of the landing buffer with the peer exchange)
+  unsigned int* counter;   // CTA arrival counter of col_update's last-block epilogue (always left at 0)
   quat* p;            // [n] tau * (M v - corrections)
   quat* pd;           // [ceil(n/MV_TC)][n]  direct partial sums of K1
   quat* pt;           // [ceil(n/MV_TR)][n]  transposed partial sums of K1
@@ -81,36 +84,30 @@ constexpr int PX_MAXW = 8;
 struct PeerX {
   int rank, world;
   size_t nmax;                              // capacity (quaternions per vector)
-  quat* bvq[PX_MAXW];                       // [g]: rank g's landing zone for the reflector, nmax + 2 quats
+  int rbmax;                                // row blocks (of PANEL_ROWS rows) per vector: flag capacity
+  quat* bx[PX_MAXW];                        // [g]: rank g's landing zone for x + record: [2 parities][nmax + 3]
   quat* ypart[PX_MAXW];                     // [g]: rank g's staging [2 parities][world][nmax]
-  unsigned long long* flags[PX_MAXW];       // [g]: rank g's flags: [0] reflector seq, [8 + 8*parity + src] partial-y seq
-  unsigned int* counters;                   // local CTA arrival counters [2]
+  unsigned long long* flags[PX_MAXW];       // [g]: rank g's flags: [0] x seq; [8 + ((parity*rbmax + rowblock)*PX_MAXW + src)] partial-y seq
   int* info;                                // local status word (bit 8 = exchange timeout)
 };
 
 // K2/K3 panel column kernels (panel.cu)
 void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st);
-void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st);
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
-// distributed variants: (1) y_local = sum of this rank's K1 partials -> w.p rows [k+1, n);
-// (2) after the all-reduce of w.p: corrections, tau scaling, partial Re(v^H p)
+// NCCL transport: (1) y_local = sum of this rank's K1 partials -> w.p rows [k+1, n);
+// (2) after the all-reduce of w.p: corrections, tau scaling, partial Re(v^H p), unpack of the column
 void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st);
 void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
-// after the broadcast of vq[k+1 .. n+2) from the owner of column k: store v into the panel, the
-// reflector storage of A and the scalars d,e,tau,alpha (vq[n] = (d,e,tau,0), vq[n+1] = alpha)
-void launch_unpack_v(const PanelWs& w, int k, int j0, cudaStream_t st);
-// peer-exchange variants (seq = monotonically increasing sequence number of this column):
-//   owner: reflector + push of v to every peer + flag;  others: wait for the flag, unpack
-void launch_reflector_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
-void launch_wait_unpack_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
-//   partial M v of the owned column blocks pushed into every rank's staging slot + flag
-void launch_reduce_partial_px(const PanelWs& w, const PeerX& px, int k, unsigned long long seq, cudaStream_t st);
-//   wait for all slots, sum them in rank order (bit-identical on every rank), correct, scale
-void launch_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
+// peer-exchange variants (seq = monotonically increasing sequence number of this column; w.x must point at the
+// landing buffer of this column's parity):
+//   owner: x rows + record pushed to every peer, then the flag;  others: finish w, last CTA waits for the flag
+void launch_col_update_px(const PanelWs& w, const PeerX& px, int k, int j0, bool owner, unsigned long long seq, cudaStream_t st);
+//   partial M v pushed per row block into every rank's staging slot + per-row-block flags, ordered sum, correction
+void launch_reduce_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
 void launch_finish_w(const PanelWs& w, int k_last, int j0, cudaStream_t st);
 // K1 quaternion-Hermitian mat-vec on the lower triangles (+ fused panel dot products)
 void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st);
-// stand-alone K1 for tests/bench: y = M[s:,s:] v (rows < s of v must be zero)
+// stand-alone K1 for tests/bench: y = M[s:,s:] v with v = w.x[s..n) as given (record u1^{-1} must be 1)
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st);
 
 // K5 (small.cu): the whole reduction of one matrix with n <= small_n_max() in one launch of one CTA (same outputs

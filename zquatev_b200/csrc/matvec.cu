@@ -86,13 +86,27 @@ ZQ_D void tile_body(const cplx* __restrict__ A, size_t lda, int n, int r0, int c
   }
 }
 
+// v[r] of the current reflector: 1 at the head row, x[r] u1^{-1} below it, 0 above (rows of a tile that lie above
+// the trailing matrix).  x and the record are read at L2 (.cg): on several GPUs they were stored by a peer, and on
+// one GPU the record is written by the last CTA of the previous kernel.
+ZQ_D quat ld_cg_quat(const quat* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  return qmake(__ldcg(q), __ldcg(q + 1));
+}
+ZQ_D quat refl_v(const quat* x, quat inv, int r, int s, int head, int n) {
+  if (r >= n || r < s) return qzero();
+  if (r == head) return qmake(cmake(1, 0), cmake(0, 0));
+  return qmul(ld_cg_quat(x + r), inv);
+}
+
 __global__ void __launch_bounds__(256, 2)
-k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __restrict__ vq, quat* __restrict__ pd,
+k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* x, int xrec, int head, quat* __restrict__ pd,
          quat* __restrict__ pt, int nI, int jfirst, int jstride, int nJ, int rev,
          // fused panel dots
          const cplx* __restrict__ pan, int nb, int ncols, int nch, int crows, quat* __restrict__ dotW, quat* __restrict__ dotV) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   pdl_enter();
+  const quat inv = ld_cg_quat(x + xrec + 2);
   if ((int)blockIdx.x >= nI) {
     // ---- panel inner products: the grid cells right of the tile columns, flattened, one per (row chunk, group of
     // 8 panel columns); warp = one panel column, lanes stride the chunk's rows ----
@@ -107,7 +121,7 @@ k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __res
     quat aW = qzero(), aV = qzero();
 #pragma unroll 4
     for (int r = ra + lane; r < rb; r += 32) {
-      const quat f = vq[r];
+      const quat f = refl_v(x, inv, r, s, head, n);
       qfma_cj(aW, qmake(wa[r], wb[r]), f);
       qfma_cj(aV, qmake(va[r], vb[r]), f);
     }
@@ -131,13 +145,13 @@ k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* __res
   const int r0 = ti.I * TR, c0 = ti.J * TC;
   if (threadIdx.x < TC) {
     const int c = c0 + threadIdx.x;
-    vcol[threadIdx.x] = (c < n) ? vq[c] : qzero();
+    vcol[threadIdx.x] = refl_v(x, inv, c, s, head, n);
   }
   quat vrow[RI], acc[RI];
 #pragma unroll
   for (int i = 0; i < RI; ++i) {
     const int r = r0 + lane + 32 * i;
-    vrow[i] = (r < n) ? vq[r] : qzero();
+    vrow[i] = refl_v(x, inv, r, s, head, n);
     acc[i] = qzero();
   }
   __syncthreads();
@@ -190,14 +204,15 @@ void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
   static const int zigzag = [] { const char* e = getenv("ZQ_K1_ZIGZAG"); return e ? atoi(e) : 1; }();
   const int rev = (zigzag && nJ > 0 && ((k - j0) & 1) == 0) ? 1 : 0;
   const int gy = nJ > 0 ? nJ : 1;
-  launch_chain(k_matvec, dim3(nI + (ndot + gy - 1) / gy, gy), dim3(256), st, w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, jfirst, w.world, gy,
+  launch_chain(k_matvec, dim3(nI + (ndot + gy - 1) / gy, gy), dim3(256), st, w.A, w.lda, n, s, (const quat*)w.x, w.xrec, s, w.pd, w.pt, nI, jfirst, w.world, gy,
                rev, w.pan, w.nb, ncols, nch > 0 ? nch : 1, crows, w.dotW, w.dotV);
 }
 
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st) {
   const int n = w.n;
   const int nI = (n - 1) / TR - s / TR + 1, nJ = (n - 1) / TC - s / TC + 1;
-  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, w.vq, w.pd, w.pt, nI, s / TC, 1, nJ, 0, w.pan, w.nb, 0, 1, DOT_MIN_ROWS, w.dotW, w.dotV);
+  // head = -1: no unit head row, v = x * record[2] for all rows >= s
+  k_matvec<<<dim3(nI, nJ), 256, 0, st>>>(w.A, w.lda, n, s, (const quat*)w.x, w.xrec, -1, w.pd, w.pt, nI, s / TC, 1, nJ, 0, w.pan, w.nb, 0, 1, DOT_MIN_ROWS, w.dotW, w.dotV);
   k_matvec_gather<<<(n - s + 255) / 256, 256, 0, st>>>(n, s, w.pd, w.pt, y);
 }
 

@@ -2,13 +2,26 @@
 //
 // Replaces the k-loop of ts::impl::panel_update (reference blocked.cc:70-414: lazy column
 // update :73-164, zlarfg :176/:345, zlartg :237, growth of T/R/S/W/Y/Z :171-413) with ONE
-// quaternion reflector per column.  Per column k = j0 + i:
-//   col_update      x = M[:,k] - V W[k,:]^* - W V[k,:]^*   (and finishes w of column k-1)
-//   reflector       v, tau, alpha from x  (zlarfg analogue, tau real)
-//   matvec (K1)     partial sums of M v   + partial W^H v, V^H v
-//   reduce_correct  p = tau (M v - V (W^H v) - W (V^H v)),  partial Re(v^H p)
+// quaternion reflector per column.  Per column k = j0 + i THREE launches:
+//   col_update      x = M[:,k] - V W[k,:]^* - W V[k,:]^*   (and finishes w of column k-1);
+//                   the LAST CTA to finish sums the norm partials and forms the reflector scalars
+//                   (zlarfg analogue, tau real): record x[xrec..xrec+3) = (d,e,tau), alpha, u1^{-1}
+//   matvec (K1)     v = x u1^{-1} is formed on the fly by every consumer (never a separate pass);
+//                   partial sums of M v  + partial W^H v, V^H v
+//   reduce_correct  p = tau (M v - V (W^H v) - W (V^H v)),  partial Re(v^H p); stores v into the panel
+//                   and into the zeroed part of column k of A (reflector storage)
 // All cross-CTA reductions go through small partial buffers summed in a fixed order, so the
 // result is bit-reproducible run to run.
+//
+// Multi-GPU (1-D block-cyclic columns, one process per GPU): the two per-column exchanges are fused
+// into these kernels over peer memory (CUDA IPC + NVLink stores, PeerX in kernels.h):
+//   * the owner's col_update pushes x (and its last CTA the scalar record) into every peer's landing
+//     buffer and publishes a sequence number; the last CTA of a non-owner's col_update waits for it,
+//     so K1 starts on data that is already there;
+//   * reduce_correct pushes its 32 rows of the local partial M v into slot [rank] of every rank,
+//     raises a per-row-block flag there, waits for the flags of the same row block from all ranks
+//     and sums the slots in rank order (bit-identical on every rank): no grid-wide barrier, no
+//     separate kernel, no NCCL call between the panel kernels.
 //
 // These kernels are latency-bound (n of each per solve): a CTA owns only PANEL_ROWS = 32 rows
 // (lane = row, coalesced column-major access) and its 8 warps split the inner loops over the
@@ -27,6 +40,14 @@ ZQ_D cplx* pan_ptr(const PanelWs& w, int which, int t) { return w.pan + ((size_t
 ZQ_D double sum_parts(const double* __restrict__ p, int np, double* sm) {
   double s = 0.0;
   for (int j = threadIdx.x; j < np; j += NT) s += p[j];
+  double v1[1] = {s};
+  block_sum<1>(v1, sm);
+  return v1[0];
+}
+// same, reading at L2 (partials written by other CTAs of the SAME grid)
+ZQ_D double sum_parts_cg(const double* p, int np, double* sm) {
+  double s = 0.0;
+  for (int j = threadIdx.x; j < np; j += NT) s += __ldcg(p + j);
   double v1[1] = {s};
   block_sum<1>(v1, sm);
   return v1[0];
@@ -50,41 +71,46 @@ ZQ_D unsigned long long ld_acquire_sys(const unsigned long long* p) {
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-ZQ_D void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+ZQ_D void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-ZQ_D quat ldcg_quat(const quat* p) {      // data written by a peer GPU: read at L2, never from a stale L1 line
-  const double2* q = reinterpret_cast<const double2*>(p);
-  return qmake(__ldcg(q), __ldcg(q + 1));
-}
-// thread 0 of the CTA waits (bounded) until *flag >= seq
+// wait (bounded) until *flag >= seq
 ZQ_D void px_wait(const unsigned long long* flag, unsigned long long seq, int* info) {
   if (*(volatile int*)info & 8) return;                                  // exchange already failed: do not wait again
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < seq) {
     if (clock64() - t0 > 8000000000LL) { atomicOr(info, 8); break; }   // ~4 s: report instead of hanging the GPU
-    __nanosleep(64);
-  }
-}
-// every thread of the CTA has issued its peer stores; once ALL CTAs of the grid have, publish seq
-ZQ_D void px_signal(const PeerX& px, unsigned int* counter, int flag_index, unsigned long long seq, bool include_self) {
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(counter, 1u);
-    if (prev == gridDim.x - 1) {
-      *(volatile unsigned int*)counter = 0u;
-      __threadfence_system();
-      for (int g = 0; g < px.world; ++g)
-        if (include_self || g != px.rank) st_release_sys(px.flags[g] + flag_index, seq);
-    }
   }
 }
 
+// reflector scalars from ||x[k+2:]||^2 and x[k+1]:  alpha = -phase(x1) ||x||,  u1 = x1 - alpha,  tau = 2|u1|^2/||u||^2
+struct Refl { quat alpha, inv; double tau, nx; };
+ZQ_D Refl make_reflector(double rest2, quat x1) {
+  Refl f;
+  f.alpha = qzero(); f.inv = qzero(); f.tau = 0.0; f.nx = 0.0;
+  const double x1n2 = qnorm2(x1);
+  const double nx2 = rest2 + x1n2;
+  if (nx2 > 0.0) {
+    f.nx = sqrt(nx2);
+    const double x1n = sqrt(x1n2);
+    const quat ph = (x1n > 0.0) ? qscale(x1, 1.0 / x1n) : qmake(cmake(1, 0), cmake(0, 0));
+    f.alpha = qscale(ph, -f.nx);
+    const double u1n = x1n + f.nx;                 // u1 = x1 - alpha = phase * (|x1| + ||x||)
+    const double u1n2 = u1n * u1n;
+    f.tau = 2.0 * u1n2 / (rest2 + u1n2);
+    f.inv = qscale(qconj(ph), 1.0 / u1n);          // u1^{-1}
+  }
+  return f;
+}
+
 // ---------------------------------------------------------------------------------------------
-// col_update: rows r in [k, n)
+// col_update: rows r in [k, n).  ROLE 0: single GPU, or owner / everybody on the NCCL transport (x and the scalar
+// record stay local).  ROLE 1: owner with the peer exchange (x rows and the record are ALSO stored into every
+// peer's landing buffer, then the sequence number is published).  ROLE 2: non-owner with the peer exchange (only
+// finishes w of column k-1; its last CTA waits until the owner's x and record have landed).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int ng_parts) {
+template <int ROLE>
+__global__ void __launch_bounds__(NT) k_col_update(PanelWs w, PeerX px, int k, int j0, int ng_parts, unsigned long long seq) {
   pdl_enter();
   const int n = w.n, i = k - j0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -92,7 +118,9 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
   __shared__ quat qW[MAX_NB_PANEL], qV[MAX_NB_PANEL];
   __shared__ quat red[NW][PR];
   __shared__ double s_red[32];
+  __shared__ int s_last;
   const bool act = r < n;
+  const size_t xpar = (ROLE != 0) ? (size_t)(k & 1) * (px.nmax + 3) : 0;   // landing buffers alternate by column parity
 
   quat wr = qzero();       // W(r, i-1) for this thread's row
   if (i > 0) {
@@ -110,163 +138,124 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int
         pan_ptr(w, 3, i - 1)[r] = wr.b;
       }
     }
-    // row-k coefficients: qconj(W(k,t)), qconj(V(k,t)), t < i
-    for (int t = threadIdx.x; t < i; t += NT) {
-      quat wk, vk;
-      if (t == i - 1) {
-        quat pk = w.p[k];
-        quat vkk = qmake(va[k], vb[k]);
-        wk = qmake(csub(pk.a, cscale(vkk.a, coef)), csub(pk.b, cscale(vkk.b, coef)));
-        vk = vkk;
-      } else {
-        wk = qmake(pan_ptr(w, 2, t)[k], pan_ptr(w, 3, t)[k]);
-        vk = qmake(pan_ptr(w, 0, t)[k], pan_ptr(w, 1, t)[k]);
+    if (ROLE != 2) {
+      // row-k coefficients: qconj(W(k,t)), qconj(V(k,t)), t < i
+      for (int t = threadIdx.x; t < i; t += NT) {
+        quat wk, vk;
+        if (t == i - 1) {
+          quat pk = w.p[k];
+          quat vkk = qmake(va[k], vb[k]);
+          wk = qmake(csub(pk.a, cscale(vkk.a, coef)), csub(pk.b, cscale(vkk.b, coef)));
+          vk = vkk;
+        } else {
+          wk = qmake(pan_ptr(w, 2, t)[k], pan_ptr(w, 3, t)[k]);
+          vk = qmake(pan_ptr(w, 0, t)[k], pan_ptr(w, 1, t)[k]);
+        }
+        qW[t] = qconj(wk);
+        qV[t] = qconj(vk);
       }
-      qW[t] = qconj(wk);
-      qV[t] = qconj(vk);
     }
   }
   __syncthreads();
 
-  quat part = qzero();     // - sum over this warp's panel columns
-  quat acol = qzero();     // A(r, k): issued before the panel loop so its HBM latency hides behind it
-  if (warp == 0 && act) acol = qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]);
-  if (act) {
+  if (ROLE != 2) {
+    quat part = qzero();     // - sum over this warp's panel columns
+    quat acol = qzero();     // A(r, k): issued before the panel loop so its HBM latency hides behind it
+    if (warp == 0 && act) acol = qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]);
+    if (act) {
 #pragma unroll 4
-    for (int t = warp; t < i; t += NW) {
-      quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
-      quat wrt = (t == i - 1) ? wr : qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
-      qfms(part, vrt, qW[t]);
-      qfms(part, wrt, qV[t]);
+      for (int t = warp; t < i; t += NW) {
+        quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
+        quat wrt = (t == i - 1) ? wr : qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
+        qfms(part, vrt, qW[t]);
+        qfms(part, wrt, qV[t]);
+      }
+    }
+    quat col = warps_sum(part, red, warp, lane);
+    double nr = 0.0;
+    if (warp == 0 && act) {
+      col = qadd(col, acol);
+      if (r == k) {
+        w.d[k] = col.a.x;
+      } else {
+        w.x[r] = col;
+        if (ROLE == 1) {
+          for (int g = 0; g < px.world; ++g)
+            if (g != px.rank) px.bx[g][xpar + r] = col;                 // NVLink peer store
+        }
+        if (r >= k + 2) nr = qnorm2(col);
+      }
+    }
+    if (warp == 0) {
+      nr = warp_sum(nr);
+      if (lane == 0) w.nrm_part[blockIdx.x] = nr;
     }
   }
-  quat col = warps_sum(part, red, warp, lane);
-  double nr = 0.0;
-  if (warp == 0 && act) {
-    col = qadd(col, acol);
-    if (r == k) {
-      w.d[k] = col.a.x;
-    } else {
-      w.x[r] = col;
-      if (r >= k + 2) nr = qnorm2(col);
-    }
-  }
-  if (warp == 0) {
-    nr = warp_sum(nr);
-    if (lane == 0) w.nrm_part[blockIdx.x] = nr;
-  }
-}
+  if (k + 1 >= n) return;                         // last diagonal entry only: no reflector
 
-// ---------------------------------------------------------------------------------------------
-// reflector: rows r in [k+1, n), 256 rows per CTA
-// ---------------------------------------------------------------------------------------------
-template <bool PX>
-__global__ void __launch_bounds__(NT) k_reflector(PanelWs w, PeerX px, int k, int j0, int nparts, unsigned long long seq) {
-  pdl_enter();
-  const int n = w.n, i = k - j0;
-  const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
-  __shared__ double s_red[32];
-  const double rest2 = sum_parts(w.nrm_part, nparts, s_red);
-  const quat x1 = w.x[k + 1];
-  const double x1n2 = qnorm2(x1);
-  const double nx2 = rest2 + x1n2;
-  quat alpha = qzero(), inv = qzero();
-  double tau = 0.0, nx = 0.0;
-  if (nx2 > 0.0) {
-    nx = sqrt(nx2);
-    const double x1n = sqrt(x1n2);
-    quat ph = (x1n > 0.0) ? qscale(x1, 1.0 / x1n) : qmake(cmake(1, 0), cmake(0, 0));
-    alpha = qscale(ph, -nx);
-    const double u1n = x1n + nx;                 // u1 = x1 - alpha = phase * (|x1| + ||x||)
-    const double u1n2 = u1n * u1n;
-    tau = 2.0 * u1n2 / (rest2 + u1n2);
-    inv = qscale(qconj(ph), 1.0 / u1n);          // u1^{-1}
+  // ---- the last CTA to arrive closes the column ----
+  if (ROLE == 1) __threadfence_system(); else __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(w.counter, 1u);
+    s_last = (prev == gridDim.x - 1);
   }
-  if (r < n) {
-    quat v;
-    if (r == k + 1) {
-      v = qmake(cmake(1, 0), cmake(0, 0));
-      w.vq[k] = qzero();
-    } else {
-      v = qmul(w.x[r], inv);                     // right scaling keeps H = I - tau v v^H Hermitian
-      w.A[(size_t)r + (size_t)k * w.lda] = v.a;  // reflector tail lives where zeros were created
-      w.A[(size_t)(n + r) + (size_t)k * w.lda] = v.b;
-    }
-    pan_ptr(w, 0, i)[r] = v.a;
-    pan_ptr(w, 1, i)[r] = v.b;
-    w.vq[r] = v;
-    if (PX) {
-      for (int g = 0; g < px.world; ++g)
-        if (g != px.rank) px.bvq[g][r] = v;           // NVLink peer store
-    }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    w.alpha[k] = alpha;
-    w.e[k] = nx;
-    w.tau[k] = tau;
-    // scalars of this column ride behind the reflector in the broadcast buffer (multi-GPU)
-    const quat sc = qmake(cmake(w.d[k], nx), cmake(tau, 0.0));
-    w.vq[n] = sc;
-    w.vq[n + 1] = alpha;
-    if (PX) {
-      for (int g = 0; g < px.world; ++g)
-        if (g != px.rank) { px.bvq[g][px.nmax] = sc; px.bvq[g][px.nmax + 1] = alpha; }
-    }
-  }
-  if (PX) px_signal(px, px.counters + 0, 0, seq, false);
-}
-
-// multi-GPU: vq[k+1 .. n+2) has just been broadcast from the owner of column k
-template <bool PX>
-__global__ void __launch_bounds__(NT) k_unpack_v(PanelWs w, PeerX px, int k, int j0, unsigned long long seq) {
-  pdl_enter();
-  const int n = w.n, i = k - j0;
-  const int r = k + 1 + blockIdx.x * NT + threadIdx.x;
-  const quat* src = PX ? px.bvq[px.rank] : w.vq;
-  const size_t sc_at = PX ? px.nmax : (size_t)n;
-  if (PX) {
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) *(volatile unsigned int*)w.counter = 0u;
+  __threadfence();
+  if (ROLE == 2) {
+    // the owner's x and scalar record for this column must have landed before K1 (next in the stream) reads them
     if (threadIdx.x == 0) px_wait(px.flags[px.rank] + 0, seq, px.info);
-    __syncthreads();
+    return;
   }
-  if (r < n) {
-    const quat v = PX ? ldcg_quat(src + r) : src[r];
-    if (PX) w.vq[r] = v;
-    pan_ptr(w, 0, i)[r] = v.a;
-    pan_ptr(w, 1, i)[r] = v.b;
-    if (r >= k + 2) {
-      w.A[(size_t)r + (size_t)k * w.lda] = v.a;
-      w.A[(size_t)(n + r) + (size_t)k * w.lda] = v.b;
+  const double rest2 = sum_parts_cg(w.nrm_part, gridDim.x, s_red);
+  if (threadIdx.x == 0) {
+    const double2* xp = reinterpret_cast<const double2*>(w.x + k + 1);
+    const quat x1 = qmake(__ldcg(xp), __ldcg(xp + 1));
+    const Refl f = make_reflector(rest2, x1);
+    const quat sc = qmake(cmake(__ldcg(w.d + k), f.nx), cmake(f.tau, 0.0));
+    w.x[w.xrec] = sc;
+    w.x[w.xrec + 1] = f.alpha;
+    w.x[w.xrec + 2] = f.inv;
+    if (ROLE == 1) {
+      for (int g = 0; g < px.world; ++g)
+        if (g != px.rank) {
+          quat* rec = px.bx[g] + xpar + px.nmax;
+          rec[0] = sc; rec[1] = f.alpha; rec[2] = f.inv;
+        }
+      __threadfence_system();
+      for (int g = 0; g < px.world; ++g)
+        if (g != px.rank) st_relaxed_sys(px.flags[g] + 0, seq);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    const quat sc = PX ? ldcg_quat(src + sc_at) : src[sc_at];
-    w.d[k] = sc.a.x;
-    w.e[k] = sc.a.y;
-    w.tau[k] = sc.b.x;
-    w.alpha[k] = PX ? ldcg_quat(src + sc_at + 1) : src[sc_at + 1];
-    w.vq[k] = qzero();
-  }
+}
+
+// v[r] of the current column from x and the scalar record (read at L2: they may have been written by a peer GPU
+// or by another CTA's last-block epilogue)
+ZQ_D quat ldcg_quat(const quat* p) {
+  const double2* q = reinterpret_cast<const double2*>(p);
+  return qmake(__ldcg(q), __ldcg(q + 1));
 }
 
 // ---------------------------------------------------------------------------------------------
 // reduce_correct: rows r in [k+1, n)
 // ---------------------------------------------------------------------------------------------
-// MODE 0: single GPU (sum all K1 partials, correct, scale).  MODE 1: multi-GPU, local part only:
-// w.p[r] = sum of THIS rank's partials.  MODE 2: multi-GPU, after the all-reduce of w.p: correct, scale.
-// MODE 3 / 4: as 1 / 2 with the peer exchange: 3 pushes the local part into slot [rank] of every rank's
-// staging buffer and signals; 4 waits for all slots and sums them in rank order.
+// MODE 0: single GPU (sum all K1 partials, correct, scale).  MODE 1: NCCL transport, local part only:
+// w.p[r] = sum of THIS rank's partials.  MODE 2: NCCL transport, after the all-reduce of w.p: correct, scale.
+// MODE 3: peer exchange, everything in one kernel: local part -> slot [rank] of every rank's staging buffer +
+// per-row-block flag; wait for the same row block of all ranks; sum in rank order; correct; scale.
+// All modes except 1 also unpack the column: d, e, tau, alpha from the scalar record and v = x u1^{-1} into the
+// panel and into the reflector storage of A.
 template <int MODE>
 __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int k, int j0, int nch, unsigned long long seq) {
   pdl_enter();
-  constexpr bool PART = (MODE == 1 || MODE == 3), FIN = (MODE == 2 || MODE == 4);
+  constexpr bool PART = (MODE == 1), FIN = (MODE == 2);
   const int n = w.n, i = k - j0, s = k + 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = s + blockIdx.x * PR + lane;
   __shared__ quat gW[MAX_NB_PANEL], gV[MAX_NB_PANEL];
   __shared__ quat red[NW][PR];
-  if (MODE == 4) {
-    if (threadIdx.x < px.world) px_wait(px.flags[px.rank] + 8 + 8 * (k & 1) + threadIdx.x, seq, px.info);
-  }
   if (!PART) {
     for (int t = threadIdx.x; t < 2 * i; t += NT) {
       const int tt = t >> 1;
@@ -282,62 +271,91 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int 
     }
   }
   quat part = qzero();
-  if (r < n) {
-    if (!FIN) {
-      const int J0 = s / MV_TC, Jlast = (n - 1) / MV_TC;
-      const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
-      const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
-      const int Ilo = max(I0, (r / MV_TC) / 2);
-      // owned column blocks only: J = jfirst, jfirst + world, ...  (world == 1: all)
-      const int jfirst = J0 + ((w.rank - J0 % w.world) + w.world) % w.world;
+  if (r < n && !FIN) {
+    const int J0 = s / MV_TC, Jlast = (n - 1) / MV_TC;
+    const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
+    const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
+    const int Ilo = max(I0, (r / MV_TC) / 2);
+    // owned column blocks only: J = jfirst, jfirst + world, ...  (world == 1: all)
+    const int jfirst = J0 + ((w.rank - J0 % w.world) + w.world) % w.world;
 #pragma unroll 4
-      for (int J = jfirst + warp * w.world; J <= Jhi; J += NW * w.world) part = qadd(part, w.pd[(size_t)J * n + r]);
-      if ((r / MV_TC) % w.world == w.rank) {   // transposed sums exist only on the owner of r's column block
+    for (int J = jfirst + warp * w.world; J <= Jhi; J += NW * w.world) part = qadd(part, w.pd[(size_t)J * n + r]);
+    if ((r / MV_TC) % w.world == w.rank) {   // transposed sums exist only on the owner of r's column block
 #pragma unroll 4
-        for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
-      }
-    } else if (warp == 0) {
-      if (MODE == 2) {
-        part = w.p[r];                         // all-reduced M v (NCCL)
-      } else {                                 // sum the G staged partials in rank order
-        const quat* yp = px.ypart[px.rank] + (size_t)(k & 1) * px.world * px.nmax;
-        for (int g = 0; g < px.world; ++g) part = qadd(part, ldcg_quat(yp + (size_t)g * px.nmax + r));
-      }
-    }
-    if (!PART) {
-#pragma unroll 4
-      for (int t = warp; t < i; t += NW) {
-        quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
-        quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
-        qfms(part, vrt, gW[t]);
-        qfms(part, wrt, gV[t]);
-      }
+      for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
     }
   }
-  quat y = warps_sum(part, red, warp, lane);
   if (MODE == 1) {
+    const quat y = warps_sum(part, red, warp, lane);
     if (warp == 0 && r < n) w.p[r] = y;
     return;
   }
   if (MODE == 3) {
-    if (warp == 0 && r < n) {
-      const size_t at = ((size_t)(k & 1) * px.world + px.rank) * px.nmax + r;
-      for (int g = 0; g < px.world; ++g) px.ypart[g][at] = y;        // own slot on every rank (NVLink stores)
+    // ---- exchange of this row block: push, flag, wait, ordered sum ----
+    const quat yl = warps_sum(part, red, warp, lane);
+    const int par = k & 1;
+    if (warp == 0) {
+      if (r < n) {
+        const size_t at = ((size_t)par * px.world + px.rank) * px.nmax + r;
+        for (int g = 0; g < px.world; ++g) px.ypart[g][at] = yl;        // own slot on every rank (NVLink stores)
+      }
+      __threadfence_system();
+      __syncwarp();
+      const size_t fl = 8 + ((size_t)par * px.rbmax + blockIdx.x) * PX_MAXW;
+      if (lane < px.world) st_relaxed_sys(px.flags[lane] + fl + px.rank, seq);
+      if (lane < px.world) px_wait(px.flags[px.rank] + fl + lane, seq, px.info);
+      __syncwarp();
+      part = qzero();
+      if (r < n) {
+        const quat* yp = px.ypart[px.rank] + (size_t)par * px.world * px.nmax;
+        for (int g = 0; g < px.world; ++g) part = qadd(part, ldcg_quat(yp + (size_t)g * px.nmax + r));
+      }
+    } else {
+      part = qzero();
     }
-    px_signal(px, px.counters + 1, 8 + 8 * (k & 1) + px.rank, seq, true);
-    return;
+    __syncthreads();                              // `red` is reused below
   }
+  if (FIN) {
+    if (warp == 0 && r < n) part = w.p[r];        // all-reduced M v (NCCL)
+  }
+  if (r < n) {
+#pragma unroll 4
+    for (int t = warp; t < i; t += NW) {
+      quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
+      quat wrt = qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
+      qfms(part, vrt, gW[t]);
+      qfms(part, wrt, gV[t]);
+    }
+  }
+  quat y = warps_sum(part, red, warp, lane);
   if (warp == 0) {
+    const quat sc = ldcg_quat(w.x + w.xrec);
     double g = 0.0;
     if (r < n) {
-      const double tau = w.tau[k];
+      const double tau = sc.b.x;
       y = qscale(y, tau);
       w.p[r] = y;
-      const quat f = w.vq[r];
+      // v of this column: stored where the next kernels (and the back-transformation) read it
+      quat f;
+      if (r == s) {
+        f = qmake(cmake(1, 0), cmake(0, 0));
+      } else {
+        f = qmul(ldcg_quat(w.x + r), ldcg_quat(w.x + w.xrec + 2));     // right scaling keeps H = I - tau v v^H Hermitian
+        w.A[(size_t)r + (size_t)k * w.lda] = f.a;                       // reflector tail lives where zeros were created
+        w.A[(size_t)(n + r) + (size_t)k * w.lda] = f.b;
+      }
+      pan_ptr(w, 0, i)[r] = f.a;
+      pan_ptr(w, 1, i)[r] = f.b;
       g = f.a.x * y.a.x + f.a.y * y.a.y + f.b.x * y.b.x + f.b.y * y.b.y;   // Re(f^H y)
     }
     g = warp_sum(g);
     if (lane == 0) w.g_part[blockIdx.x] = g;
+    if (blockIdx.x == 0 && lane == 0) {
+      w.d[k] = sc.a.x;
+      w.e[k] = sc.a.y;
+      w.tau[k] = sc.b.x;
+      w.alpha[k] = ldcg_quat(w.x + w.xrec + 1);
+    }
   }
 }
 
@@ -389,13 +407,14 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k;                    // rows k..n-1
   const int ng = (k > j0) ? cdiv(w.n - k, PR) : 0;   // g_part written by reduce_correct of column k-1 (rows k..n-1)
-  launch_chain(k_col_update, dim3(cdiv(rows, PR)), dim3(NT), st, w, k, j0, ng);
+  launch_chain(k_col_update<0>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, ng, 0ull);
 }
 
-void launch_reflector(const PanelWs& w, int k, int j0, cudaStream_t st) {
-  const int rows = w.n - k - 1;
-  const int nparts = cdiv(w.n - k, PR);        // nrm_part written by col_update (rows k..n-1)
-  launch_chain(k_reflector<false>, dim3(cdiv(rows, NT)), dim3(NT), st, w, PeerX{}, k, j0, nparts, 0ull);
+void launch_col_update_px(const PanelWs& w, const PeerX& px, int k, int j0, bool owner, unsigned long long seq, cudaStream_t st) {
+  const int rows = w.n - k;
+  const int ng = (k > j0) ? cdiv(w.n - k, PR) : 0;
+  if (owner) launch_chain(k_col_update<1>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, ng, seq);
+  else       launch_chain(k_col_update<2>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, ng, seq);
 }
 
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
@@ -415,29 +434,9 @@ void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   launch_chain(k_reduce_correct<2>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, 0ull);
 }
 
-void launch_unpack_v(const PanelWs& w, int k, int j0, cudaStream_t st) {
+void launch_reduce_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  launch_chain(k_unpack_v<false>, dim3(cdiv(rows, NT)), dim3(NT), st, w, PeerX{}, k, j0, 0ull);
-}
-
-void launch_reflector_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
-  const int rows = w.n - k - 1;
-  launch_chain(k_reflector<true>, dim3(cdiv(rows, NT)), dim3(NT), st, w, px, k, j0, cdiv(w.n - k, PR), seq);
-}
-
-void launch_wait_unpack_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
-  const int rows = w.n - k - 1;
-  launch_chain(k_unpack_v<true>, dim3(cdiv(rows, NT)), dim3(NT), st, w, px, k, j0, seq);
-}
-
-void launch_reduce_partial_px(const PanelWs& w, const PeerX& px, int k, unsigned long long seq, cudaStream_t st) {
-  const int rows = w.n - k - 1;
-  launch_chain(k_reduce_correct<3>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, k, 0, seq);
-}
-
-void launch_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
-  const int rows = w.n - k - 1;
-  launch_chain(k_reduce_correct<4>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, cdiv(rows, dot_chunk_rows(rows)), seq);
+  launch_chain(k_reduce_correct<3>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, cdiv(rows, dot_chunk_rows(rows)), seq);
 }
 
 void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {

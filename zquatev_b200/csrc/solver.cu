@@ -48,6 +48,9 @@ struct Plan {
   double* eig_dev = nullptr;
   cudaEvent_t ev[6] = {};
   cudaEvent_t ev_gather = nullptr;   // multi-GPU: recorded before the NCCL gather of the eigenvector shards
+  cudaStream_t cs = nullptr;         // host-pointer mode: D2H of finished eigenvector column blocks overlaps the next block
+  cudaEvent_t ev_chunk[4] = {};      //   block c back-transformed (recorded on the solver's stream, awaited by cs)
+  cudaEvent_t ev_copy = nullptr;     //   all downloads issued on cs are complete
   cudaEvent_t done = nullptr;        // recorded at the end of every solve: the next user of this workspace waits on it,
   bool done_valid = false;           // so an asynchronous solve on another stream cannot race with it
   double gather_ms = 0;
@@ -101,8 +104,19 @@ static int nccl_fail(ncclResult_t r, int line) {
 }
 #define ZQ_NCCL_CHECK(expr) do { ncclResult_t _r = (expr); if (_r != ncclSuccess) return nccl_fail(_r, __LINE__); } while (0)
 
-static std::mutex g_mu;
-static Plan* g_plan = nullptr;
+// A handle owns a cache of plans (device workspaces, one per (n, nb)) on ONE device and its own lock: solves through
+// different handles do not serialise on each other (the reference allocates and frees its workspace inside every
+// call, zquatev.cc:63-66 "TODO"; here a caller that alternates between sizes keeps all of them warm).
+struct Handle {
+  int device = -1;
+  std::mutex mu;
+  std::vector<Plan*> plans;          // most recently used first
+  Plan* last = nullptr;              // plan of the last solve (phase timings)
+  size_t max_plans = 4;
+};
+static std::mutex g_mu;              // default-handle table, batched lanes, communicator set-up
+static std::mutex g_dist_mu;         // collective solves share the one communicator of the process
+static Handle* g_default[64] = {};   // default handle per device: the reference-shaped entries use it
 static bool g_profile = false;
 
 static void plan_free(Plan* p) {
@@ -113,6 +127,9 @@ static void plan_free(Plan* p) {
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->ev_gather) cudaEventDestroy(p->ev_gather);
   if (p->done) cudaEventDestroy(p->done);
+  for (auto& e : p->ev_chunk) if (e) cudaEventDestroy(e);
+  if (p->ev_copy) cudaEventDestroy(p->ev_copy);
+  if (p->cs) cudaStreamDestroy(p->cs);
   for (auto& e : p->k1ev) cudaEventDestroy(e);
   for (auto& e : p->k4ev) cudaEventDestroy(e);
   delete p;
@@ -125,65 +142,127 @@ bool pdl_enabled() {
   return on;
 }
 
+// layout of a plan's device slab (offsets in bytes); also what zquatev_b200_workspace_query reports
+struct Slab {
+  size_t pan, x, p, cnt, pd, pt, dW, dV, np, gp, d, e, tau, al, G, L, R, P, T, T12, S12, ST, Y, TY, YP, s, bis, info, eig;
+  size_t bytes, yp_elems;
+};
+static Slab slab_layout(int n, int nb) {
+  Slab o{};
+  const size_t N = (size_t)n;
+  size_t bytes = 0;
+  auto take = [&](size_t b) { size_t at = bytes; bytes += (b + 255) & ~(size_t)255; return at; };
+  o.pan = take(4 * (size_t)nb * N * sizeof(cplx));
+  o.x = take((N + 3) * sizeof(quat)); o.p = take(N * sizeof(quat)); o.cnt = take(256);
+  o.pd = take((size_t)cdiv(n, MV_TC) * N * sizeof(quat));
+  o.pt = take((size_t)cdiv(n, MV_TR) * N * sizeof(quat));
+  const size_t nch = DOT_MAX_CHUNKS + 1;
+  o.dW = take(nch * nb * sizeof(quat)); o.dV = take(nch * nb * sizeof(quat));
+  const size_t nparts = (size_t)cdiv(n, PANEL_ROWS) + 1;
+  o.np = take(nparts * 8); o.gp = take(nparts * 8);
+  o.d = take(N * 8); o.e = take(N * 8); o.tau = take(N * 8); o.al = take(N * sizeof(quat));
+  o.G = take(N * nb * sizeof(quat));
+  o.L = take(2 * N * 4 * nb * sizeof(cplx)); o.R = take(N * 4 * nb * sizeof(cplx));
+  // P, Y, TY are sized for TWO merged panels (ZQ_BT_PAIR); T12 / S12 / ST hold the merged T factor and its cross term
+  o.P = take(2 * N * 4 * nb * sizeof(cplx)); o.T = take((size_t)cdiv(n, nb) * 4 * nb * nb * sizeof(cplx));   // T of every panel
+  o.T12 = take((size_t)16 * nb * nb * sizeof(cplx)); o.S12 = take((size_t)4 * nb * nb * sizeof(cplx));
+  o.ST = take((size_t)4 * nb * nb * sizeof(cplx));
+  o.Y = take((size_t)4 * nb * N * sizeof(cplx)); o.TY = take((size_t)4 * nb * N * sizeof(cplx));
+  o.yp_elems = (size_t)YP_PARTS * 2 * nb * N;
+  o.YP = take(o.yp_elems * sizeof(cplx));
+  o.s = take(N * sizeof(quat)); o.bis = take((N + 8) * 8); o.info = take(256); o.eig = take(N * 8);
+  o.bytes = bytes;
+  return o;
+}
+static unsigned long long plan_slab_bytes(int n, int nb) { return slab_layout(n, nb).bytes; }
+
 static int plan_create(int n, int nb, Plan** out) {
   Plan* p = new Plan();
   p->n = n;
   p->nb = nb;
   cudaError_t e0 = cudaGetDevice(&p->device);
   if (e0 != cudaSuccess) { delete p; return zq_cuda_fail(e0, __FILE__, __LINE__); }
-  const size_t N = (size_t)n;
-  size_t bytes = 0;
-  auto take = [&](size_t b) { size_t o = bytes; bytes += (b + 255) & ~(size_t)255; return o; };
-  const size_t o_pan = take(4 * (size_t)nb * N * sizeof(cplx));
-  const size_t o_x = take(N * sizeof(quat)), o_vq = take((N + 2) * sizeof(quat)), o_p = take(N * sizeof(quat));
-  const size_t o_pd = take((size_t)cdiv(n, MV_TC) * N * sizeof(quat));
-  const size_t o_pt = take((size_t)cdiv(n, MV_TR) * N * sizeof(quat));
-  const size_t nch = DOT_MAX_CHUNKS + 1;
-  const size_t o_dW = take(nch * nb * sizeof(quat)), o_dV = take(nch * nb * sizeof(quat));
-  const size_t nparts = (size_t)cdiv(n, PANEL_ROWS) + 1;
-  const size_t o_np = take(nparts * 8), o_gp = take(nparts * 8);
-  const size_t o_d = take(N * 8), o_e = take(N * 8), o_tau = take(N * 8), o_al = take(N * sizeof(quat));
-  const size_t o_G = take(N * nb * sizeof(quat));
-  const size_t o_L = take(2 * N * 4 * nb * sizeof(cplx)), o_R = take(N * 4 * nb * sizeof(cplx));
-  // P, Y, TY are sized for TWO merged panels (ZQ_BT_PAIR); T12 / S12 / ST hold the merged T factor and its cross term
-  const size_t o_P = take(2 * N * 4 * nb * sizeof(cplx)), o_T = take((size_t)cdiv(n, nb) * 4 * nb * nb * sizeof(cplx));   // T of every panel
-  const size_t o_T12 = take((size_t)16 * nb * nb * sizeof(cplx)), o_S12 = take((size_t)4 * nb * nb * sizeof(cplx));
-  const size_t o_ST = take((size_t)4 * nb * nb * sizeof(cplx));
-  const size_t o_Y = take((size_t)4 * nb * N * sizeof(cplx)), o_TY = take((size_t)4 * nb * N * sizeof(cplx));
-  p->yp_elems = (size_t)YP_PARTS * 2 * nb * N;
-  const size_t o_YP = take(p->yp_elems * sizeof(cplx));
-  const size_t o_s = take(N * sizeof(quat)), o_bis = take((N + 8) * 8), o_info = take(256), o_eig = take(N * 8);
-  cudaError_t e = cudaMalloc(&p->slab, bytes);
+  const Slab o = slab_layout(n, nb);
+  p->yp_elems = o.yp_elems;
+  cudaError_t e = cudaMalloc(&p->slab, o.bytes);
   if (e == cudaSuccess) e = small_prepare();
+  if (e == cudaSuccess) e = cudaMemset(p->slab + o.cnt, 0, 256);     // arrival counter: every kernel leaves it at 0
   if (e != cudaSuccess) { delete p; return zq_cuda_fail(e, __FILE__, __LINE__); }
   char* b = p->slab;
   PanelWs& w = p->pw;
   w.n = n; w.nb = nb; w.lda = 0; w.A = nullptr; w.rank = 0; w.world = 1;
-  w.pan = (cplx*)(b + o_pan); w.x = (quat*)(b + o_x); w.vq = (quat*)(b + o_vq); w.p = (quat*)(b + o_p);
-  w.pd = (quat*)(b + o_pd); w.pt = (quat*)(b + o_pt); w.dotW = (quat*)(b + o_dW); w.dotV = (quat*)(b + o_dV);
-  w.nrm_part = (double*)(b + o_np); w.g_part = (double*)(b + o_gp);
-  w.d = (double*)(b + o_d); w.e = (double*)(b + o_e); w.tau = (double*)(b + o_tau); w.alpha = (quat*)(b + o_al);
-  w.G = (quat*)(b + o_G);
-  p->L = (cplx*)(b + o_L); p->R = (cplx*)(b + o_R); p->P = (cplx*)(b + o_P); p->T = (cplx*)(b + o_T);
-  p->T12 = (cplx*)(b + o_T12); p->S12 = (cplx*)(b + o_S12); p->ST = (cplx*)(b + o_ST);
-  p->Y = (cplx*)(b + o_Y); p->TY = (cplx*)(b + o_TY); p->YP = (cplx*)(b + o_YP); p->s = (quat*)(b + o_s); p->bis = (double*)(b + o_bis);
-  p->info_dev = (int*)(b + o_info); p->eig_dev = (double*)(b + o_eig);
+  w.pan = (cplx*)(b + o.pan); w.x = (quat*)(b + o.x); w.xrec = n; w.counter = (unsigned int*)(b + o.cnt); w.p = (quat*)(b + o.p);
+  w.pd = (quat*)(b + o.pd); w.pt = (quat*)(b + o.pt); w.dotW = (quat*)(b + o.dW); w.dotV = (quat*)(b + o.dV);
+  w.nrm_part = (double*)(b + o.np); w.g_part = (double*)(b + o.gp);
+  w.d = (double*)(b + o.d); w.e = (double*)(b + o.e); w.tau = (double*)(b + o.tau); w.alpha = (quat*)(b + o.al);
+  w.G = (quat*)(b + o.G);
+  p->L = (cplx*)(b + o.L); p->R = (cplx*)(b + o.R); p->P = (cplx*)(b + o.P); p->T = (cplx*)(b + o.T);
+  p->T12 = (cplx*)(b + o.T12); p->S12 = (cplx*)(b + o.S12); p->ST = (cplx*)(b + o.ST);
+  p->Y = (cplx*)(b + o.Y); p->TY = (cplx*)(b + o.TY); p->YP = (cplx*)(b + o.YP); p->s = (quat*)(b + o.s); p->bis = (double*)(b + o.bis);
+  p->info_dev = (int*)(b + o.info); p->eig_dev = (double*)(b + o.eig);
   for (auto& ev : p->ev) cudaEventCreate(&ev);
   cudaEventCreate(&p->ev_gather);
   cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming);
+  for (auto& ev : p->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming);
   *out = p;
   return 0;
 }
 
-static int get_plan(int n, int nb, Plan** out) {
+static void handle_clear(Handle* h) {
+  if (h->plans.empty()) return;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cur != h->device) cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (Plan* p : h->plans) plan_free(p);
+  h->plans.clear();
+  h->last = nullptr;
+  if (cur != h->device && cur >= 0) cudaSetDevice(cur);
+}
+
+// handle lock held.  Looks the plan up, else creates it; the least recently used plans are dropped beyond max_plans
+// or when the device runs out of memory.
+static int get_plan(Handle* h, int n, int nb, Plan** out) {
+  for (size_t i = 0; i < h->plans.size(); ++i) {
+    Plan* p = h->plans[i];
+    if (p->n == n && p->nb == nb) {
+      h->plans.erase(h->plans.begin() + i);
+      h->plans.insert(h->plans.begin(), p);
+      *out = p;
+      return 0;
+    }
+  }
+  auto drop_lru = [&]() {
+    Plan* v = h->plans.back();
+    h->plans.pop_back();
+    if (v->done_valid) cudaEventSynchronize(v->done);
+    if (h->last == v) h->last = nullptr;
+    plan_free(v);
+  };
+  while (h->plans.size() >= h->max_plans) drop_lru();
+  Plan* p = nullptr;
+  int rc = plan_create(n, nb, &p);
+  while (rc == -(1000 + (int)cudaErrorMemoryAllocation) && !h->plans.empty()) {
+    cudaGetLastError();
+    drop_lru();
+    rc = plan_create(n, nb, &p);
+  }
+  if (rc) return rc;
+  h->plans.insert(h->plans.begin(), p);
+  *out = p;
+  return 0;
+}
+
+static int default_handle(Handle** out) {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return zq_cuda_fail(e, __FILE__, __LINE__);
-  if (g_plan && g_plan->n == n && g_plan->nb == nb && g_plan->device == dev) { *out = g_plan; return 0; }
-  if (g_plan) { cudaDeviceSynchronize(); plan_free(g_plan); g_plan = nullptr; }
-  int rc = plan_create(n, nb, &g_plan);
-  *out = g_plan;
-  return rc;
+  std::lock_guard<std::mutex> lk(g_mu);
+  Handle*& h = g_default[dev & 63];
+  if (!h) { h = new Handle(); h->device = dev; }
+  *out = h;
+  return 0;
 }
 
 // The panel (V_a,V_b,W_a,W_b: 4*nb*n complex, 67 MB at n = 16384) is re-read by col_update, the dot CTAs and
@@ -226,7 +305,6 @@ static void l2_window(cudaStream_t st, void* base, size_t bytes) {
 static void tridiagonalise(Plan* p, cudaStream_t st) {
   const PanelWs& w = p->pw;
   const int n = w.n, nb = w.nb;
-  cudaMemsetAsync(w.vq, 0, (size_t)n * sizeof(quat), st);
   cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
@@ -251,13 +329,12 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
     for (int i = 0; i < kb; ++i) {
       const int k = j0 + i;
-      launch_col_update(w, k, j0, st);
-      launch_reflector(w, k, j0, st);
+      launch_col_update(w, k, j0, st);          // x, d_k; its last CTA forms the reflector scalars
       if (prof) cudaEventRecord(p->k1ev[2 * k], st);
-      launch_matvec(w, k, j0, st);
+      launch_matvec(w, k, j0, st);              // v = x u1^{-1} on the fly
       if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
-      launch_reduce_correct(w, k, j0, st);
-      p->launches += 4;
+      launch_reduce_correct(w, k, j0, st);      // p, g; stores v
+      p->launches += 3;
     }
     launch_finish_w(w, j0 + kb - 1, j0, st);
     const int r0 = j0 + kb, m = n - r0;
@@ -276,13 +353,16 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
   if (n >= 2048) l2_window(st, w.pan, 0);
 }
 
-// Exchange-buffer layout per rank: [bvq: nmax+2 quats][ypart: 2*PX_MAXW*nmax quats][flags: 64 u64][counters: 16 u32]
-static size_t px_bytes(size_t nmax) { return ((nmax + 2) + 2 * (size_t)PX_MAXW * nmax) * sizeof(quat) + 64 * 8 + 16 * 4; }
+// Exchange-buffer layout per rank: [bx: 2 parities x (nmax+3) quats][ypart: 2*PX_MAXW*nmax quats][flags: 8 + 2*rbmax*PX_MAXW u64]
+static int px_rbmax(size_t nmax) { return (int)((nmax + PANEL_ROWS - 1) / PANEL_ROWS) + 1; }
+static size_t px_bytes(size_t nmax) {
+  return (2 * (nmax + 3) + 2 * (size_t)PX_MAXW * nmax) * sizeof(quat) + (8 + 2 * (size_t)px_rbmax(nmax) * PX_MAXW) * 8;
+}
 
 static void px_fill(PeerX& px, int g, char* base, size_t nmax) {
-  px.bvq[g] = (quat*)base;
-  px.ypart[g] = (quat*)base + (nmax + 2);
-  px.flags[g] = (unsigned long long*)((quat*)base + (nmax + 2) + 2 * (size_t)PX_MAXW * nmax);
+  px.bx[g] = (quat*)base;
+  px.ypart[g] = (quat*)base + 2 * (nmax + 3);
+  px.flags[g] = (unsigned long long*)((quat*)base + 2 * (nmax + 3) + 2 * (size_t)PX_MAXW * nmax);
 }
 
 static void px_teardown() {
@@ -313,7 +393,7 @@ static int px_setup(int rank, int world, size_t nmax) {
   ZQ_CUDA_CHECK(cudaMemcpy(all.data(), dbuf, 64 * (size_t)world, cudaMemcpyDeviceToHost));
   cudaFree(dbuf);
   PeerX px{};
-  px.rank = rank; px.world = world; px.nmax = nmax;
+  px.rank = rank; px.world = world; px.nmax = nmax; px.rbmax = px_rbmax(nmax);
   int ok = 1;
   for (int g = 0; g < world; ++g) {
     char* base = g_xb;
@@ -334,7 +414,6 @@ static int px_setup(int rank, int world, size_t nmax) {
   ZQ_CUDA_CHECK(cudaMemcpy(&ok, dflag, sizeof(int), cudaMemcpyDeviceToHost));
   cudaFree(dflag);
   if (!ok) { px_teardown(); return 0; }
-  px.counters = (unsigned int*)((char*)px.flags[rank] + 64 * 8);
   g_px = px;
   g_seq_base = 0;
   return 0;
@@ -343,9 +422,12 @@ static int px_setup(int rank, int world, size_t nmax) {
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU reduction: D and E are distributed 1-D block-cyclic by 64-column blocks
 // (every rank keeps the full array but only its own blocks are kept up to date).  Per column: the
-// owner forms the reflector and broadcasts it (one NCCL broadcast of 32 m + 64 bytes), every rank
-// multiplies its own column blocks (K1), the partial products are all-reduced (32 m bytes), and the
-// panel algebra is replicated.  The trailing update touches only the owned blocks: no exchange.
+// owner forms x and the reflector scalars and hands them to everybody, every rank multiplies its own
+// column blocks (K1), the partial products are summed over the ranks, and the panel algebra is
+// replicated.  The trailing update touches only the owned blocks: no exchange.
+// Transport 2 (default): both exchanges are peer-memory stores issued by the panel kernels themselves
+// (panel.cu), three launches per column as on one GPU.  Transport 1 (ZQ_DIST_NCCL=1 or peers that
+// cannot be mapped): one ncclBroadcast of x + record and one ncclAllReduce of the partial M v per column.
 // ---------------------------------------------------------------------------------------------
 static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   PanelWs& w = p->pw;
@@ -357,17 +439,22 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
     p->k1ev.resize(2 * (size_t)n);
     for (size_t i = old; i < p->k1ev.size(); ++i) cudaEventCreate(&p->k1ev[i]);
   }
+  if (prof && p->k4ev.size() < 2 * (size_t)(n / nb + 1)) {
+    const size_t old = p->k4ev.size();
+    p->k4ev.resize(2 * (size_t)(n / nb + 1));
+    for (size_t i = old; i < p->k4ev.size(); ++i) cudaEventCreate(&p->k4ev[i]);
+  }
+  quat* const x_local = w.x;
   w.rank = g_rank;
   w.world = G;
   struct Restore {              // the cached plan must never keep the distributed geometry, whatever the exit path
-    PanelWs& w;
-    ~Restore() { w.rank = 0; w.world = 1; }
-  } restore{w};
+    PanelWs& w; quat* x; int n;
+    ~Restore() { w.rank = 0; w.world = 1; w.x = x; w.xrec = n; }
+  } restore{w, x_local, n};
   const bool use_px = g_px.world == G && (size_t)n <= g_px.nmax;
   if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
   PeerX px = g_px;
   px.info = p->info_dev;
-  cudaMemsetAsync(w.vq, 0, (size_t)(n + 2) * sizeof(quat), st);
   cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
@@ -376,29 +463,27 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
     const int owner = (j0 / nb) % G;
     for (int i = 0; i < kb; ++i) {
       const int k = j0 + i, m = n - k - 1;
-      launch_col_update(w, k, j0, st);
       if (use_px) {
-        // fused exchange: the kernels push v / the partial products straight into the peers' HBM over NVLink
+        // x and the record of column k live in this rank's landing buffer of parity k & 1 (owner: written locally)
         const unsigned long long seq = g_seq_base + (unsigned long long)k + 1ull;
-        if (owner == g_rank) launch_reflector_px(w, px, k, j0, seq, st);
-        else launch_wait_unpack_px(w, px, k, j0, seq, st);
+        w.x = px.bx[g_rank] + (size_t)(k & 1) * (px.nmax + 3);
+        w.xrec = (int)px.nmax;
+        launch_col_update_px(w, px, k, j0, owner == g_rank, seq, st);
         if (prof) cudaEventRecord(p->k1ev[2 * k], st);
         launch_matvec(w, k, j0, st);
         if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
-        launch_reduce_partial_px(w, px, k, seq, st);
-        launch_correct_px(w, px, k, j0, seq, st);
-        p->launches += 5;
+        launch_reduce_correct_px(w, px, k, j0, seq, st);
+        p->launches += 3;
       } else {
-        if (owner == g_rank) launch_reflector(w, k, j0, st);
-        ZQ_NCCL_CHECK(g_nccl.Broadcast(w.vq + k + 1, w.vq + k + 1, (size_t)4 * (m + 2), ncclDouble, owner, g_comm, st));
-        launch_unpack_v(w, k, j0, st);
+        launch_col_update(w, k, j0, st);           // non-owners: finishes w; their x is overwritten by the broadcast
+        ZQ_NCCL_CHECK(g_nccl.Broadcast(w.x + k + 1, w.x + k + 1, (size_t)4 * (m + 3), ncclDouble, owner, g_comm, st));
         if (prof) cudaEventRecord(p->k1ev[2 * k], st);
         launch_matvec(w, k, j0, st);
         if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
         launch_reduce_partial(w, k, st);
         ZQ_NCCL_CHECK(g_nccl.AllReduce(w.p + k + 1, w.p + k + 1, (size_t)4 * m, ncclDouble, ncclSum, g_comm, st));
         launch_correct(w, k, j0, st);
-        p->launches += 7;
+        p->launches += 6;
       }
     }
     launch_finish_w(w, j0 + kb - 1, j0, st);
@@ -409,11 +494,15 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
       const int b0 = r0 / MV_TC, nblk = (m + MV_TC - 1) / MV_TC;
       const int cb0 = ((g_rank - b0 % G) + G) % G;
       const int ncb = cb0 >= nblk ? 0 : (nblk - 1 - cb0) / G + 1;
+      if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
       launch_zgemm_cb(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
                       w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, cb0, G, ncb, st);
+      if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb) + 1], st);
       p->launches += 3;
     }
   }
+  w.x = x_local;
+  w.xrec = n;
   launch_col_update(w, n - 1, n - 1, st);          // d[n-1]: valid on the owner of the last column block
   ZQ_NCCL_CHECK(g_nccl.Broadcast(w.d + n - 1, w.d + n - 1, 1, ncclDouble, ((n - 1) / nb) % G, g_comm, st));
   p->launches += 1;
@@ -489,8 +578,6 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
   const int n = w.n, nb = w.nb;
   if (n < 2 || ncols <= 0) return;
   const int last = ((n - 2) / nb) * nb;
-  launch_build_T_all(w, p->T, st);
-  p->launches += 1;
   const char* pe = getenv("ZQ_BT_PAIR");                 // read at every solve (tests switch it)
   const bool pair = pe && atoi(pe) != 0;
   for (int j0 = last; j0 >= 0; j0 -= nb) {
@@ -540,7 +627,44 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
 }
 
 // full solve on device-resident operands.  Dfull: 2n x 2n complex (ld), left half = input.
-static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, int dist, int gather, cudaStream_t st) {
+// Host-pointer mode: where finished eigenvector column blocks go (downloaded on the plan's copy stream while the next
+// block is back-transformed).
+struct HostSink { cplx* D; size_t ld2; };
+
+// Eigenvector column blocks of the single-GPU host-pointer solve: a large first block, then blocks small enough that
+// (a) the download of block c hides behind the back-transformation of block c+1 (PCIe moves a column ~10x faster than
+// the GEMMs produce one) and (b) only the last, smallest block's download is exposed.  ZQ_E2E_CHUNKS="a,b,c" (column
+// counts, the first absorbs the remainder) overrides.
+static int sink_chunks(int n, int* nc) {
+  int cnt = 1;
+  nc[0] = n;
+  if (const char* e = getenv("ZQ_E2E_CHUNKS")) {
+    int v[4] = {0, 0, 0, 0}, k = 0;
+    for (const char* q = e; *q && k < 4;) {
+      v[k++] = atoi(q);
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    int rest = 0;
+    for (int i = 1; i < k; ++i) rest += v[i] > 0 ? v[i] : 0;
+    if (k >= 1 && rest < n) {
+      cnt = 0;
+      nc[cnt++] = n - rest;
+      for (int i = 1; i < k; ++i) if (v[i] > 0) nc[cnt++] = v[i];
+    }
+    return cnt;
+  }
+  if (n < 2048) return 1;
+  int last = n / 16;
+  if (last < 512) last = 512;
+  last = (last + 63) & ~63;
+  if (n >= 8192) { nc[0] = n - 3 * last; nc[1] = 2 * last; nc[2] = last; cnt = 3; }
+  else           { nc[0] = n - last; nc[1] = last; cnt = 2; }
+  return cnt;
+}
+
+static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, int dist, int gather, cudaStream_t st,
+                        const HostSink* sink = nullptr) {
   const int n = p->n;
   PanelWs& w = p->pw;
   w.A = Dfull;
@@ -587,9 +711,36 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
       col0 = g_rank * per < n ? g_rank * per : n;
       ncols = (col0 + per <= n) ? per : n - col0;
     } else if (ncols <= 0 || col0 < 0 || col0 + ncols > n) { col0 = 0; ncols = n; }
-    launch_scale_Z(n, ncols, Z, (size_t)n, perm + col0, p->s, X + (size_t)col0 * ld, ld, st);
-    backtransform(p, X + (size_t)col0 * ld, ld, ncols, st);
-    launch_swap_pairing(n, ncols, Dfull + (size_t)col0 * ld, ld, st);
+    launch_build_T_all(w, p->T, st);            // compact-WY T factor of every panel, once
+    p->launches += 1;
+    int cnc[4] = {ncols, 0, 0, 0};
+    const int nchunk = (sink && !dist && p->timing && p->cs) ? sink_chunks(ncols, cnc) : 1;
+    int c0 = col0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int nc = cnc[c];
+      launch_scale_Z(n, nc, Z, (size_t)n, perm + c0, p->s, X + (size_t)c0 * ld, ld, st);
+      backtransform(p, X + (size_t)c0 * ld, ld, nc, st);
+      launch_swap_pairing(n, nc, Dfull + (size_t)c0 * ld, ld, st);
+      p->launches += 2;
+      if (sink && !dist && p->cs) {             // columns [c0, c0+nc) and their Kramers partners are final: download now
+        if (c == nchunk - 1 && p->timing) cudaEventRecord(p->ev[4], st);
+        ZQ_CUDA_CHECK(cudaEventRecord(p->ev_chunk[c], st));
+        ZQ_CUDA_CHECK(cudaStreamWaitEvent(p->cs, p->ev_chunk[c], 0));
+        const size_t w16 = (size_t)2 * n * sizeof(cplx);
+        ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)c0 * sink->ld2, sink->ld2 * sizeof(cplx), Dfull + (size_t)c0 * ld, ld * sizeof(cplx), w16,
+                                        (size_t)nc, cudaMemcpyDeviceToHost, p->cs));
+        ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)(n + c0) * sink->ld2, sink->ld2 * sizeof(cplx), Dfull + (size_t)(n + c0) * ld,
+                                        ld * sizeof(cplx), w16, (size_t)nc, cudaMemcpyDeviceToHost, p->cs));
+      }
+      c0 += nc;
+    }
+    if (sink && !dist && p->cs) {               // the solver's stream continues (eigenvalues, status) after the last download
+      ZQ_CUDA_CHECK(cudaEventRecord(p->ev_copy, p->cs));
+      ZQ_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_copy, 0));
+      cudaError_t e2 = cudaGetLastError();
+      if (e2 != cudaSuccess) return zq_cuda_fail(e2, __FILE__, __LINE__);
+      return 0;
+    }
     if (dist && gather) {                       // every rank ends with all 2n columns
       if (p->timing) { cudaEventRecord(p->ev_gather, st); p->gather_ms = 0.0; }
       const int per = (n + g_world - 1) / g_world;
@@ -665,20 +816,59 @@ static int check_args(int n2, void* D, int ld2, double* eig) {
   return 0;
 }
 
-static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* opt) {
+// H2D of what the solver reads: only the LOWER triangles of A (Hermitian) and B (antisymmetric), column block by
+// column block -- half the bytes of the left half (the reference needs both triangles; for a valid
+// quaternion-Hermitian input they carry the same information).
+constexpr int UP_BLK = 256;
+static int upload_lower(cplx* Dfull, size_t ld, const cplx* D, size_t ld2, int n, cudaStream_t st) {
+  if (n < 1024) {               // small: one strided copy of the left half
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(Dfull, ld * sizeof(cplx), D, ld2 * sizeof(cplx), (size_t)2 * n * sizeof(cplx), (size_t)n,
+                                    cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  for (int c0 = 0; c0 < n; c0 += UP_BLK) {
+    const int nc = (UP_BLK < n - c0) ? UP_BLK : n - c0;
+    const size_t rows = (size_t)(n - c0);
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(Dfull + c0 + (size_t)c0 * ld, ld * sizeof(cplx), D + c0 + (size_t)c0 * ld2, ld2 * sizeof(cplx),
+                                    rows * sizeof(cplx), (size_t)nc, cudaMemcpyHostToDevice, st));
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(Dfull + n + c0 + (size_t)c0 * ld, ld * sizeof(cplx), D + n + c0 + (size_t)c0 * ld2, ld2 * sizeof(cplx),
+                                    rows * sizeof(cplx), (size_t)nc, cudaMemcpyHostToDevice, st));
+  }
+  return 0;
+}
+
+static int plan_host_staging(Plan* p) {
+  const size_t n2 = 2 * (size_t)p->n;
+  if (!p->Dfull) ZQ_CUDA_CHECK(cudaMalloc(&p->Dfull, n2 * n2 * sizeof(cplx)));
+  if (!p->cs) ZQ_CUDA_CHECK(cudaStreamCreateWithFlags(&p->cs, cudaStreamNonBlocking));
+  return 0;
+}
+
+static int solve_any(Handle* h, int n2, void* D, int ld2, double* eig, const zq_options* opt) {
   int rc = check_args(n2, D, ld2, eig);
   if (rc) return rc;
   if (n2 == 0) return 0;
+  if (!h) {
+    rc = default_handle(&h);
+    if (rc) return rc;
+  }
   const int n = n2 / 2;
   const int jobz = opt ? opt->jobz : 1;
   const int devp = opt ? opt->device_ptrs : 0;
+  const int dist = opt ? opt->dist : 0;
   int nb = (opt && opt->nb > 0) ? opt->nb : DEFAULT_NB;
   if (nb > MAX_NB) nb = MAX_NB;
   cudaStream_t st = opt ? (cudaStream_t)opt->stream : (cudaStream_t)0;
-  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = -1;
+  ZQ_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev != h->device) return -7;                 // a handle is bound to the device it was created on
+  std::unique_lock<std::mutex> dlk(g_dist_mu, std::defer_lock);
+  if (dist) dlk.lock();                            // one communicator per process: collective solves are serialised
+  std::lock_guard<std::mutex> lk(h->mu);
   Plan* p = nullptr;
-  rc = get_plan(n, nb, &p);
+  rc = get_plan(h, n, nb, &p);
   if (rc) return rc;
+  h->last = p;
   // the workspace may still be in use by an asynchronous solve enqueued on ANOTHER stream: order after it
   if (p->done_valid) ZQ_CUDA_CHECK(cudaStreamWaitEvent(st, p->done, 0));
   struct DoneMark {             // every exit path (errors included) leaves the completion event behind the enqueued work
@@ -686,7 +876,7 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
     ~DoneMark() { if (cudaEventRecord(p->done, st) == cudaSuccess) p->done_valid = true; else cudaGetLastError(); }
   } done_mark{p, st};
   if (devp) {
-    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, opt ? opt->dist : 0, 1, st);
+    rc = solve_device(p, (cplx*)D, (size_t)ld2, eig, jobz, opt ? opt->col0 : 0, opt ? opt->ncols : 0, dist, 1, st);
     if (rc) return rc;
     if (opt && opt->sync) {
       int info = 0;
@@ -699,18 +889,20 @@ static int solve_any(int n2, void* D, int ld2, double* eig, const zq_options* op
   }
   // host pointers: stage through a device copy of the full 2n x 2n array
   const size_t ld = (size_t)n2;
-  if (!p->Dfull) ZQ_CUDA_CHECK(cudaMalloc(&p->Dfull, ld * n2 * sizeof(cplx)));
-  cudaEventRecord(p->ev[0], st);
-  const int dist_in = opt ? opt->dist : 0;
-  if (!dist_in || g_rank == 0 || !g_comm)
-    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(p->Dfull, ld * sizeof(cplx), D, (size_t)ld2 * sizeof(cplx), (size_t)n2 * sizeof(cplx),
-                                    (size_t)n, cudaMemcpyHostToDevice, st));
-  if (dist_in && g_comm)     // the ranks share the host links: rank 0 uploads once, NVLink carries the input to the others
-    ZQ_NCCL_CHECK(g_nccl.Broadcast(p->Dfull, p->Dfull, (size_t)2 * n * ld, ncclDouble, 0, g_comm, st));
-  const int dist = opt ? opt->dist : 0;
-  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, dist, 1, st);
+  rc = plan_host_staging(p);
   if (rc) return rc;
-  if (jobz) {
+  cudaEventRecord(p->ev[0], st);
+  if (!dist || g_rank == 0 || !g_comm) {
+    rc = upload_lower(p->Dfull, ld, (const cplx*)D, (size_t)ld2, n, st);
+    if (rc) return rc;
+  }
+  if (dist && g_comm)        // the ranks share the host links: rank 0 uploads once, NVLink carries the input to the others
+    ZQ_NCCL_CHECK(g_nccl.Broadcast(p->Dfull, p->Dfull, (size_t)2 * n * ld, ncclDouble, 0, g_comm, st));
+  const HostSink sink{(cplx*)D, (size_t)ld2};
+  const bool piped = jobz && !dist;                // finished column blocks are downloaded while the next is computed
+  rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, dist, 1, st, piped ? &sink : nullptr);
+  if (rc) return rc;
+  if (jobz && !piped) {
     if (dist && opt->host_result == 1 && g_rank != 0) {
       // distributed host result: this rank downloads only its own eigenvector columns (and their Kramers partners)
       const int per = (n + g_world - 1) / g_world;
@@ -808,10 +1000,85 @@ bool lane_capture(Lane& L, int n) {
 
 extern "C" {
 
-int zquatev_b200(int n2, void* D, int ld2, double* eig) { return solve_any(n2, D, ld2, eig, nullptr); }
+int zquatev_b200(int n2, void* D, int ld2, double* eig) { return solve_any(nullptr, n2, D, ld2, eig, nullptr); }
 
 int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt) {
-  return solve_any(n2, D, ld2, eig, opt);
+  return solve_any(nullptr, n2, D, ld2, eig, opt);
+}
+
+// ---- handles: explicit workspace ownership (the reference's per-call allocation is zquatev.cc:63-66) ----
+int zquatev_b200_create(zq_handle_t* out) {
+  if (!out) return -1;
+  int dev = -1;
+  ZQ_CUDA_CHECK(cudaGetDevice(&dev));
+  Handle* h = new Handle();
+  h->device = dev;
+  *out = reinterpret_cast<zq_handle_t>(h);
+  return 0;
+}
+
+int zquatev_b200_destroy(zq_handle_t hh) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return -1;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    handle_clear(h);
+  }
+  delete h;
+  return 0;
+}
+
+int zquatev_b200_solve(zq_handle_t hh, int n2, void* D, int ld2, double* eig, const zq_options* opt) {
+  if (!hh) return -1;
+  return solve_any(reinterpret_cast<Handle*>(hh), n2, D, ld2, eig, opt);
+}
+
+// Allocates (or finds) the plan of this size now, including the tridiagonal D&C workspace when eigenvectors are
+// wanted and the 2n x 2n device staging + copy stream of the host-pointer mode: the first solve of that size then
+// allocates nothing.
+int zquatev_b200_reserve(zq_handle_t hh, int n2, const zq_options* opt) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (n2 <= 0 || (n2 & 1)) return -2;
+  int rc = 0;
+  if (!h) { rc = default_handle(&h); if (rc) return rc; }
+  int dev = -1;
+  ZQ_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev != h->device) return -7;
+  int nb = (opt && opt->nb > 0) ? opt->nb : DEFAULT_NB;
+  if (nb > MAX_NB) nb = MAX_NB;
+  std::lock_guard<std::mutex> lk(h->mu);
+  Plan* p = nullptr;
+  rc = get_plan(h, n2 / 2, nb, &p);
+  if (rc) return rc;
+  if (!opt || opt->jobz) {
+    if (!p->dc) p->dc = dc_create(n2 / 2);
+    if (!p->dc) return zq_cuda_fail(cudaGetLastError(), __FILE__, __LINE__);
+  }
+  if (!opt || !opt->device_ptrs) rc = plan_host_staging(p);
+  return rc;
+}
+
+// Bytes a plan of this size holds: device workspace (panels, partial sums, GEMM operands, D&C when jobz = 1, the
+// 2n x 2n staging array when the operands are host pointers).  No allocation happens here.
+int zquatev_b200_workspace_query(int n2, const zq_options* opt, unsigned long long* device_bytes) {
+  if (n2 < 0 || (n2 & 1) || !device_bytes) return -1;
+  const int n = n2 / 2;
+  int nb = (opt && opt->nb > 0) ? opt->nb : DEFAULT_NB;
+  if (nb > MAX_NB) nb = MAX_NB;
+  unsigned long long b = plan_slab_bytes(n, nb);
+  if (!opt || opt->jobz) b += dc_bytes(n);
+  if (!opt || !opt->device_ptrs) b += 16ull * (unsigned long long)n2 * (unsigned long long)n2;
+  *device_bytes = b;
+  return 0;
+}
+
+int zquatev_b200_handle_phases(zq_handle_t hh, double ms[8]) {
+  Handle* h = reinterpret_cast<Handle*>(hh);
+  if (!h) return 0;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (!h->last) return 0;
+  for (int i = 0; i < 8; ++i) ms[i] = h->last->phase_ms[i];
+  return 1;
 }
 
 // Batched entry: see the lane machinery above.  The problems are handed out by an atomic counter to a few host
@@ -997,43 +1264,65 @@ void zquatev_b200_dist_finalize(void) {
 
 void zquatev_b200_release(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_plan) { cudaDeviceSynchronize(); plan_free(g_plan); g_plan = nullptr; }
+  for (Handle* h : g_default)
+    if (h) { std::lock_guard<std::mutex> lk2(h->mu); handle_clear(h); }
   lanes_free();
 }
 
+// plan of the last solve through the default handle of the current device
+static Plan* last_default_plan(std::unique_lock<std::mutex>& hold) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  Handle* h = nullptr;
+  { std::lock_guard<std::mutex> lk(g_mu); h = g_default[dev & 63]; }
+  if (!h) return nullptr;
+  hold = std::unique_lock<std::mutex>(h->mu);
+  return h->last;
+}
+
 int zquatev_b200_last_phases(double ms[8]) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_plan) return 0;
-  for (int i = 0; i < 8; ++i) ms[i] = g_plan->phase_ms[i];
+  std::unique_lock<std::mutex> hold;
+  Plan* p = last_default_plan(hold);
+  if (!p) return 0;
+  for (int i = 0; i < 8; ++i) ms[i] = p->phase_ms[i];
   return 1;
 }
 
 void zquatev_b200_set_profiling(int on) { g_profile = on != 0; }
 
 double zquatev_b200_last_gather_ms(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  return g_plan ? g_plan->gather_ms : 0.0;
+  std::unique_lock<std::mutex> hold;
+  Plan* p = last_default_plan(hold);
+  return p ? p->gather_ms : 0.0;
 }
 
 double zquatev_b200_last_trailing_ms(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  return g_plan ? g_plan->k4_ms : 0.0;
+  std::unique_lock<std::mutex> hold;
+  Plan* p = last_default_plan(hold);
+  return p ? p->k4_ms : 0.0;
 }
 
 const char* zquatev_b200_version(void) { return "zquatev_b200 0.2 sm_100a nb=64"; }
 
 // ---- test doors ------------------------------------------------------------------------------
 int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, void* y, int reps, double* ms) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = nullptr;
+  int rc = default_handle(&h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mu);
   Plan* p = nullptr;
-  int rc = get_plan(n, DEFAULT_NB, &p);
+  rc = get_plan(h, n, DEFAULT_NB, &p);
   if (rc) return rc;
   PanelWs& w = p->pw;
   w.A = (cplx*)A;
   w.lda = (size_t)lda;
   cudaStream_t st = 0;
-  ZQ_CUDA_CHECK(cudaMemsetAsync(w.vq, 0, (size_t)n * sizeof(quat), st));
-  ZQ_CUDA_CHECK(cudaMemcpyAsync(w.vq + s, (const quat*)v + s, (size_t)(n - s) * sizeof(quat), cudaMemcpyDeviceToDevice, st));
+  // v itself goes into x; the record's u1^{-1} is the quaternion 1
+  const double one[12] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
+  ZQ_CUDA_CHECK(cudaMemsetAsync(w.x, 0, (size_t)n * sizeof(quat), st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(w.x + s, (const quat*)v + s, (size_t)(n - s) * sizeof(quat), cudaMemcpyDeviceToDevice, st));
+  ZQ_CUDA_CHECK(cudaMemcpyAsync(w.x + w.xrec, one, sizeof(one), cudaMemcpyHostToDevice, st));
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
   launch_matvec_only(w, s, (quat*)y, st);   // warm-up + result
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
@@ -1115,11 +1404,14 @@ int zq_test_bisect(int n, const double* d, const double* e, double* w) {
 }
 
 int zq_test_tridiag(int n, int nb, void* A, long long lda, double* d, double* e, double* tau, double* alpha) {
-  std::lock_guard<std::mutex> lk(g_mu);
+  Handle* h = nullptr;
+  int rc = default_handle(&h);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(h->mu);
   Plan* p = nullptr;
   if (nb <= 0) nb = DEFAULT_NB;
   if (nb > MAX_NB) nb = MAX_NB;
-  int rc = get_plan(n, nb, &p);
+  rc = get_plan(h, n, nb, &p);
   if (rc) return rc;
   cudaStream_t st = 0;
   p->pw.A = (cplx*)A;

@@ -24,7 +24,7 @@ namespace zq {
 namespace {
 
 
-int g_allow_3m = 1;   // set per solve by the driver: small problems use the conventional product
+thread_local int g_allow_3m = 1;   // set per solve by the calling thread (launches happen on that thread): small problems use the conventional product
 
 ZQ_D void cp_async16(void* smem, const void* gmem, bool pred) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
