@@ -82,6 +82,24 @@ def main():
         out.append({"transport": "peer", "n": n, "ok": bool(ok), "eig_dev_vs_reference": dev_gold, "res": q["residual"], "res_reference": float(meta[1]),
                     "orth": q["orthogonality"], "orth_reference": float(meta[2]), "pair": q["pairing"], "ranks_agree": bool(same),
                     "bitwise_reproducible": repro})
+    # values-only collective solve (BASELINE config 4 shape): 1-D block-cyclic reduction + bisection sharded by
+    # eigenvalue index ranges with one all-gather of n doubles
+    for n, seed in [(65, 3), (333, 5), (1030, 8)]:
+        M = O.gen_sym(n, seed)
+        buf0 = torch.from_numpy(np.asfortranarray(M).T.copy()).cuda()
+        e_full = torch.zeros(n, dtype=torch.float64, device="cuda")
+        b1 = buf0.clone()
+        i0 = z.zquatev_device(2 * n, b1.data_ptr(), 2 * n, e_full.data_ptr(), nb=64)
+        e_val = torch.zeros(n, dtype=torch.float64, device="cuda")
+        b2 = buf0.clone()
+        i1 = z.zquatev_device(2 * n, b2.data_ptr(), 2 * n, e_val.data_ptr(), jobz=0, nb=64, dist=True)
+        nrm = e_full.abs().max().item()
+        dev_rel = (e_val - e_full).abs().max().item() / nrm
+        lst = [torch.zeros_like(e_val) for _ in range(world)]
+        dist.all_gather(lst, e_val)
+        same = all(torch.equal(lst[0], t) for t in lst)
+        ok = i0 == 0 and i1 == 0 and dev_rel <= 1e-12 and same and bool(torch.all(e_val[1:] >= e_val[:-1]))
+        out.append({"transport": "peer", "mode": "values-only", "n": n, "ok": bool(ok), "eig_dev": dev_rel, "ranks_agree": bool(same)})
     zd.finalize()
     if rank == 0:
         print("DIST_RESULT " + json.dumps(out), flush=True)

@@ -146,23 +146,15 @@ __global__ void __launch_bounds__(256) k_scale_Z(int n, const double* __restrict
   const int j = blockIdx.y;
   const int r = blockIdx.x * 256 + threadIdx.x;
   if (r >= n) return;
-  const double z = Z[(size_t)r + (size_t)perm[j] * ldz];
+  int src = perm[j];
+  if ((unsigned)src >= (unsigned)n) src = j;          // a failed eigensolver (info > 0) must not turn into a wild read
+  const double z = Z[(size_t)r + (size_t)src * ldz];
   const quat q = s[r];
   X[(size_t)r + (size_t)j * ldx] = cscale(q.a, z);
   X[(size_t)(n + r) + (size_t)j * ldx] = cscale(q.b, z);
 }
 
-// K10: right half = Theta(left half): columns n+j = (-conj(V_j); conj(U_j))   (zquatev.cc:93-98)
-__global__ void __launch_bounds__(256) k_pairing(int n, cplx* Out, size_t ld) {
-  const int j = blockIdx.y;
-  const int r = blockIdx.x * 256 + threadIdx.x;
-  if (r >= n) return;
-  const cplx u = Out[(size_t)r + (size_t)j * ld];
-  const cplx v = Out[(size_t)(n + r) + (size_t)j * ld];
-  Out[(size_t)r + (size_t)(n + j) * ld] = cneg(cconj(v));
-  Out[(size_t)(n + r) + (size_t)(n + j) * ld] = cconj(u);
-}
-
+// K10: in-place pairing: X sits in the right half; left half <- X, right half <- Theta(X) = (-conj(V); conj(U))   (zquatev.cc:93-98)
 __global__ void __launch_bounds__(256) k_swap_pairing(int n, cplx* Out, size_t ld) {
   const int j = blockIdx.y;
   const int r = blockIdx.x * 256 + threadIdx.x;
@@ -174,6 +166,18 @@ __global__ void __launch_bounds__(256) k_swap_pairing(int n, cplx* Out, size_t l
   L[n + r] = v;
   R[r] = cneg(cconj(v));
   R[n + r] = cconj(u);
+}
+
+// K10, host-pointer pipeline: X (in the right half) has already been downloaded into the caller's LEFT half; turn it into
+// Theta(X) in place for the download into the caller's right half.  The left half of the device array (the reflector
+// storage the remaining column blocks still need) is not touched.
+__global__ void __launch_bounds__(256) k_theta_inplace(int n, cplx* R, size_t ld) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= n) return;
+  cplx* c = R + (size_t)blockIdx.y * ld;
+  const cplx u = c[r], v = c[n + r];
+  c[r] = cneg(cconj(v));
+  c[n + r] = cconj(u);
 }
 
 // deterministic split-K reduction: Y = parts[0] + parts[1] + ... (fixed order)
@@ -194,6 +198,13 @@ __global__ void k_check_finite(int n, const double* d, const double* e, int* fla
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (!isfinite(d[i]) || (i + 1 < n && !isfinite(e[i]))) atomicOr(flag, 1);
+}
+// A non-finite tridiagonal (NaN / Inf in the input) is reported through info; the eigensolver behind it then runs on
+// a zero matrix instead of NaNs, whose comparisons would leave its index arrays (ranks, permutations) undefined.
+__global__ void k_sanitize(int n, double* d, double* e, const int* flag) {
+  if (!(*flag & 1)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { d[i] = 0.0; e[i] = 0.0; }
 }
 
 }  // namespace
@@ -237,19 +248,21 @@ void launch_sum_parts(size_t count, int nparts, const cplx* parts, size_t stride
   k_sum_parts<<<(unsigned)blocks, 256, 0, st>>>(count, nparts, parts, stride, Y);
 }
 
-void launch_pairing(int n, cplx* Out, size_t ld, cudaStream_t st) {
-  dim3 g((n + 255) / 256, n);
-  k_pairing<<<g, 256, 0, st>>>(n, Out, ld);
-}
-
 void launch_swap_pairing(int n, int ncols, cplx* Out, size_t ld, cudaStream_t st) {
   if (ncols <= 0) return;
   dim3 g((n + 255) / 256, ncols);
   k_swap_pairing<<<g, 256, 0, st>>>(n, Out, ld);
 }
 
-void launch_check_finite(int n, const double* d, const double* e, int* flag, cudaStream_t st) {
+void launch_theta_inplace(int n, int ncols, cplx* R, size_t ld, cudaStream_t st) {
+  if (ncols <= 0) return;
+  dim3 g((n + 255) / 256, ncols);
+  k_theta_inplace<<<g, 256, 0, st>>>(n, R, ld);
+}
+
+void launch_check_finite(int n, double* d, double* e, int* flag, cudaStream_t st) {
   k_check_finite<<<(n + 255) / 256, 256, 0, st>>>(n, d, e, flag);
+  k_sanitize<<<(n + 255) / 256, 256, 0, st>>>(n, d, e, flag);
 }
 
 }  // namespace zq

@@ -48,9 +48,9 @@ ZQ_D int sturm(int n, const double* __restrict__ d, const double* __restrict__ e
 }
 
 __global__ void __launch_bounds__(128) k_bisect(int n, const double* __restrict__ d, const double* __restrict__ e2,
-                                                const double* __restrict__ bnd, double* w) {
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= n) return;
+                                                const double* __restrict__ bnd, double* w, int jlo, int jhi) {
+  const int j = jlo + blockIdx.x * 128 + threadIdx.x;
+  if (j >= jhi) return;
   double lo = bnd[0], hi = bnd[1];
   const double nrm = bnd[2];
   const double pivmin = DBL_MIN * fmax(1.0, nrm * nrm);
@@ -70,13 +70,16 @@ __global__ void k_sq(int n, const double* e, double* e2) {
 
 }  // namespace
 
-// scratch: needs n + 3 doubles
-void launch_bisect(int n, const double* d, const double* e, double* w, double* scratch, cudaStream_t st) {
+// scratch: needs n + 3 doubles.  Eigenvalue indices [jlo, jhi) only (multi-GPU: one index range per rank, SURVEY.md 8e;
+// every index is an independent bisection, so the ranges need no exchange until the final all-gather).
+void launch_bisect(int n, const double* d, const double* e, double* w, double* scratch, cudaStream_t st, int jlo, int jhi) {
   double* e2 = scratch;
   double* bnd = scratch + n;
+  if (jhi < 0 || jhi > n) jhi = n;
+  if (jlo < 0) jlo = 0;
   k_sq<<<(n + 255) / 256, 256, 0, st>>>(n, e, e2);
   k_gersh<<<1, 1024, 0, st>>>(n, d, e, bnd);
-  k_bisect<<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bnd, w);
+  if (jhi > jlo) k_bisect<<<(jhi - jlo + 127) / 128, 128, 0, st>>>(n, d, e2, bnd, w, jlo, jhi);
 }
 
 }  // namespace zq

@@ -19,6 +19,8 @@ __host__ __device__ inline int dot_chunk_rows(int rows) {
   while ((rows + r - 1) / r > DOT_MAX_CHUNKS) r *= 2;
   return r;
 }
+constexpr int K1_TPB_MAX = 8;      // column blocks per K1 CTA (a run); k1_tpb(m) picks 1, 2 or 4 from the trailing size
+int k1_tpb(int m);
 constexpr int ROWS_PER_CTA = 256;
 constexpr int PANEL_ROWS = 32;      // rows per CTA of the latency-bound panel kernels
 constexpr int MAX_NB_PANEL = 64;    // largest panel width
@@ -35,11 +37,11 @@ inline bool first_use_on_this_device(std::atomic<unsigned long long>& mask) {
 // serialization attribute, see pdl_enter() in common.cuh
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_chain_smem(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -47,6 +49,10 @@ inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, c
   cfg.attrs = at;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+  return launch_chain_smem(kern, grid, block, 0, st, static_cast<Args&&>(args)...);
 }
 
 struct PanelWs {
@@ -108,7 +114,7 @@ void launch_finish_w(const PanelWs& w, int k_last, int j0, cudaStream_t st);
 // K1 quaternion-Hermitian mat-vec on the lower triangles (+ fused panel dot products)
 void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st);
 // stand-alone K1 for tests/bench: y = M[s:,s:] v with v = w.x[s..n) as given (record u1^{-1} must be 1)
-void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st);
+void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st, bool gather = true);
 
 // K5 (small.cu): the whole reduction of one matrix with n <= small_n_max() in one launch of one CTA (same outputs
 // as the K1-K4 chain: d, e, tau, alpha, reflector tails in A, Gram columns G).  small_n_max() = ZQ_SMALL_N (read at
@@ -160,11 +166,11 @@ void launch_build_T_all(const PanelWs& w, cplx* Tall, cudaStream_t st);
 void launch_phase_chain(int n, const quat* alpha, const double* e, quat* s, cudaStream_t st);
 void launch_scale_Z(int n, int ncols, const double* Z, size_t ldz, const int* perm, const quat* s, cplx* X, size_t ldx,
                     cudaStream_t st);
-// K10 pairing: right half = Theta(left half)
-void launch_pairing(int n, cplx* Out, size_t ld, cudaStream_t st);
-// in-place variant used by the driver: X sits in the RIGHT half (columns n..2n-1); on exit the left
+// K10 pairing, in place: X sits in the RIGHT half (columns n..2n-1); on exit the left
 // half holds (U;V) = X and the right half Theta(X) = (-conj V; conj U)
 void launch_swap_pairing(int n, int ncols, cplx* Out, size_t ld, cudaStream_t st);
+// R (2n x ncols block of X) <- Theta(R) in place (host-pointer pipeline: X itself has been downloaded already)
+void launch_theta_inplace(int n, int ncols, cplx* R, size_t ld, cudaStream_t st);
 
 // K8 tridiagonal divide & conquer (dc.cu).  d,e: n ; Z: n x n (ldz) ; on exit w ascending = d[perm[.]]
 struct DcWs;
@@ -182,9 +188,15 @@ int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, do
 
 // K9 eigenvalues only: Sturm bisection
 // scratch: n + 3 doubles
-void launch_bisect(int n, const double* d, const double* e, double* w, double* scratch, cudaStream_t st);
+void launch_bisect(int n, const double* d, const double* e, double* w, double* scratch, cudaStream_t st, int jlo = 0, int jhi = -1);
+
+// input scaling (scale.cu): largest entry brought into [sqrt(safmin/eps), sqrt(eps/safmin)] like LAPACK's zheev driver
+size_t scale_scratch_doubles(int n);
+void launch_scale_input(cplx* A, size_t lda, int n, double* scratch, cudaStream_t st);
+void launch_unscale_eig(int n, double* eig, const double* scratch, cudaStream_t st);
 
 // misc
-void launch_check_finite(int n, const double* d, const double* e, int* flag, cudaStream_t st);
+// sets bit 0 of *flag when d / e hold NaN or Inf, and then zeroes them (the eigensolver must not see NaNs)
+void launch_check_finite(int n, double* d, double* e, int* flag, cudaStream_t st);
 
 }  // namespace zq

@@ -248,7 +248,7 @@ ZQ_D quat ldcg_quat(const quat* p) {
 // All modes except 1 also unpack the column: d, e, tau, alpha from the scalar record and v = x u1^{-1} into the
 // panel and into the reflector storage of A.
 template <int MODE>
-__global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int k, int j0, int nch, unsigned long long seq) {
+__global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int k, int j0, int nch, int tpb, unsigned long long seq) {
   pdl_enter();
   constexpr bool PART = (MODE == 1), FIN = (MODE == 2);
   const int n = w.n, i = k - j0, s = k + 1;
@@ -276,10 +276,14 @@ __global__ void __launch_bounds__(NT) k_reduce_correct(PanelWs w, PeerX px, int 
     const int I0 = s / MV_TR, I1 = (n - 1) / MV_TR;
     const int Jhi = min(2 * (r / MV_TR) + 1, Jlast);
     const int Ilo = max(I0, (r / MV_TC) / 2);
-    // owned column blocks only: J = jfirst, jfirst + world, ...  (world == 1: all)
-    const int jfirst = J0 + ((w.rank - J0 % w.world) + w.world) % w.world;
+    // direct sums: one slot per RUN of tpb owned column blocks (matvec.cu); owned blocks J = rank + q*world
+    const int G = w.world;
+    const int jfirst = J0 + ((w.rank - J0 % G) + G) % G;
+    if (jfirst <= Jhi) {
+      const int Rlo = (jfirst / G) / tpb, Rhi = ((Jhi - w.rank) / G) / tpb;
 #pragma unroll 4
-    for (int J = jfirst + warp * w.world; J <= Jhi; J += NW * w.world) part = qadd(part, w.pd[(size_t)J * n + r]);
+      for (int R = Rlo + warp; R <= Rhi; R += NW) part = qadd(part, w.pd[(size_t)R * n + r]);
+    }
     if ((r / MV_TC) % w.world == w.rank) {   // transposed sums exist only on the owner of r's column block
 #pragma unroll 4
       for (int I = Ilo + warp; I <= I1; I += NW) part = qadd(part, w.pt[(size_t)I * n + r]);
@@ -420,23 +424,23 @@ void launch_col_update_px(const PanelWs& w, const PeerX& px, int k, int j0, bool
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nch = cdiv(rows, dot_chunk_rows(rows));
-  launch_chain(k_reduce_correct<0>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, 0ull);
+  launch_chain(k_reduce_correct<0>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, k1_tpb(rows), 0ull);
 }
 
 void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  launch_chain(k_reduce_correct<1>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, k, 0, 0ull);
+  launch_chain(k_reduce_correct<1>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, k, 0, k1_tpb(rows), 0ull);
 }
 
 void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nch = cdiv(rows, dot_chunk_rows(rows));
-  launch_chain(k_reduce_correct<2>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, 0ull);
+  launch_chain(k_reduce_correct<2>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, 1, 0ull);
 }
 
 void launch_reduce_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  launch_chain(k_reduce_correct<3>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, cdiv(rows, dot_chunk_rows(rows)), seq);
+  launch_chain(k_reduce_correct<3>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, cdiv(rows, dot_chunk_rows(rows)), k1_tpb(rows), seq);
 }
 
 void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {

@@ -42,6 +42,8 @@ struct Plan {
   size_t yp_elems = 0;       // capacity of YP (split-K partial products of Y = Phi(V)^H X)
   quat* s = nullptr;
   double* bis = nullptr;
+  double* dcv = nullptr;     // n + 8*PX_MAXW doubles: all-gather staging of the sharded bisection
+  double* scl = nullptr;     // input scaling: (sigma, 1/sigma) + partial maxima
   int* info_dev = nullptr;
   DcWs* dc = nullptr;
   cplx* Dfull = nullptr;     // host-pointer mode staging, 2n x 2n
@@ -144,7 +146,7 @@ bool pdl_enabled() {
 
 // layout of a plan's device slab (offsets in bytes); also what zquatev_b200_workspace_query reports
 struct Slab {
-  size_t pan, x, p, cnt, pd, pt, dW, dV, np, gp, d, e, tau, al, G, L, R, P, T, T12, S12, ST, Y, TY, YP, s, bis, info, eig;
+  size_t pan, x, p, cnt, pd, pt, dW, dV, np, gp, d, e, tau, al, G, L, R, P, T, T12, S12, ST, Y, TY, YP, s, bis, info, eig, scl, dcv;
   size_t bytes, yp_elems;
 };
 static Slab slab_layout(int n, int nb) {
@@ -171,6 +173,8 @@ static Slab slab_layout(int n, int nb) {
   o.yp_elems = (size_t)YP_PARTS * 2 * nb * N;
   o.YP = take(o.yp_elems * sizeof(cplx));
   o.s = take(N * sizeof(quat)); o.bis = take((N + 8) * 8); o.info = take(256); o.eig = take(N * 8);
+  o.scl = take(scale_scratch_doubles(n) * 8);
+  o.dcv = take((N + 8 * PX_MAXW) * 8);
   o.bytes = bytes;
   return o;
 }
@@ -199,7 +203,7 @@ static int plan_create(int n, int nb, Plan** out) {
   p->L = (cplx*)(b + o.L); p->R = (cplx*)(b + o.R); p->P = (cplx*)(b + o.P); p->T = (cplx*)(b + o.T);
   p->T12 = (cplx*)(b + o.T12); p->S12 = (cplx*)(b + o.S12); p->ST = (cplx*)(b + o.ST);
   p->Y = (cplx*)(b + o.Y); p->TY = (cplx*)(b + o.TY); p->YP = (cplx*)(b + o.YP); p->s = (quat*)(b + o.s); p->bis = (double*)(b + o.bis);
-  p->info_dev = (int*)(b + o.info); p->eig_dev = (double*)(b + o.eig);
+  p->info_dev = (int*)(b + o.info); p->eig_dev = (double*)(b + o.eig); p->scl = (double*)(b + o.scl); p->dcv = (double*)(b + o.dcv);
   for (auto& ev : p->ev) cudaEventCreate(&ev);
   cudaEventCreate(&p->ev_gather);
   cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming);
@@ -676,6 +680,8 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   zgemm_allow_3m(n >= 1024);
   cudaMemsetAsync(p->info_dev, 0, sizeof(int), st);
   if (p->timing) cudaEventRecord(p->ev[1], st);
+  launch_scale_input(Dfull, ld, n, p->scl, st);     // zlascl analogue: a no-op pass unless max|a| is outside [1e-146, 1e145]
+  p->launches += 3;
   if (dist) {
     if (!g_comm) return -6;
     const int rc = tridiagonalise_dist(p, st);
@@ -686,7 +692,20 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   launch_check_finite(n, w.d, w.e, p->info_dev, st);
   if (p->timing) cudaEventRecord(p->ev[2], st);
   if (!jobz) {
-    launch_bisect(n, w.d, w.e, eig_dev, p->bis, st);
+    if (dist && g_world > 1) {
+      // K9 sharded by eigenvalue index ranges: rank g bisects indices [g per, (g+1) per), then one
+      // all-gather of per doubles per rank (staged in the bisection scratch so that a ragged tail needs no padding
+      // in the caller's array)
+      const int per = (n + g_world - 1) / g_world;
+      const int jlo = g_rank * per < n ? g_rank * per : n, jhi = (jlo + per < n) ? jlo + per : n;
+      double* stage = p->dcv;                     // per * world doubles
+      launch_bisect(n, w.d, w.e, stage, p->bis, st, jlo, jhi);   // writes stage[j], j in [jlo, jhi)
+      ZQ_NCCL_CHECK(g_nccl.AllGather(stage + (size_t)g_rank * per, stage, (size_t)per, ncclDouble, g_comm, st));
+      ZQ_CUDA_CHECK(cudaMemcpyAsync(eig_dev, stage, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    } else {
+      launch_bisect(n, w.d, w.e, eig_dev, p->bis, st);
+    }
+    launch_unscale_eig(n, eig_dev, p->scl, st);
     if (p->timing) cudaEventRecord(p->ev[3], st);
     if (p->timing) cudaEventRecord(p->ev[4], st);
   } else {
@@ -702,7 +721,8 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
               }};
     int rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st, dist ? &dd : nullptr);
     if (rc) return rc;
-    p->launches += dc_launches(p->dc) + 3;
+    launch_unscale_eig(n, eig_dev, p->scl, st);
+    p->launches += dc_launches(p->dc) + 4;
     if (p->timing) cudaEventRecord(p->ev[3], st);
     cplx* X = Dfull + (size_t)n * ld;          // right half is scratch until the pairing
     launch_phase_chain(n, w.alpha, w.e, p->s, st);
@@ -714,27 +734,37 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     launch_build_T_all(w, p->T, st);            // compact-WY T factor of every panel, once
     p->launches += 1;
     int cnc[4] = {ncols, 0, 0, 0};
-    const int nchunk = (sink && !dist && p->timing && p->cs) ? sink_chunks(ncols, cnc) : 1;
+    const int nchunk = (sink && !dist && p->cs) ? sink_chunks(ncols, cnc) : 1;
+    const bool piped = sink && !dist && p->cs;
     int c0 = col0;
     for (int c = 0; c < nchunk; ++c) {
       const int nc = cnc[c];
       launch_scale_Z(n, nc, Z, (size_t)n, perm + c0, p->s, X + (size_t)c0 * ld, ld, st);
       backtransform(p, X + (size_t)c0 * ld, ld, nc, st);
-      launch_swap_pairing(n, nc, Dfull + (size_t)c0 * ld, ld, st);
-      p->launches += 2;
-      if (sink && !dist && p->cs) {             // columns [c0, c0+nc) and their Kramers partners are final: download now
+      p->launches += 1;
+      if (!piped) {
+        launch_swap_pairing(n, nc, Dfull + (size_t)c0 * ld, ld, st);
+        p->launches += 1;
+      } else {
+        // Host-pointer pipeline.  X = (U; V) of these columns is final and sits in the RIGHT half of the device array;
+        // the left half still holds the reflectors the next blocks need, so nothing is swapped on the device.  On the
+        // copy stream: X -> caller's left half, X <- Theta(X) in place (K10), X -> caller's right half -- while the
+        // solver's stream back-transforms the next block.
         if (c == nchunk - 1 && p->timing) cudaEventRecord(p->ev[4], st);
         ZQ_CUDA_CHECK(cudaEventRecord(p->ev_chunk[c], st));
         ZQ_CUDA_CHECK(cudaStreamWaitEvent(p->cs, p->ev_chunk[c], 0));
         const size_t w16 = (size_t)2 * n * sizeof(cplx);
-        ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)c0 * sink->ld2, sink->ld2 * sizeof(cplx), Dfull + (size_t)c0 * ld, ld * sizeof(cplx), w16,
-                                        (size_t)nc, cudaMemcpyDeviceToHost, p->cs));
-        ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)(n + c0) * sink->ld2, sink->ld2 * sizeof(cplx), Dfull + (size_t)(n + c0) * ld,
-                                        ld * sizeof(cplx), w16, (size_t)nc, cudaMemcpyDeviceToHost, p->cs));
+        cplx* Xc = X + (size_t)c0 * ld;
+        ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)c0 * sink->ld2, sink->ld2 * sizeof(cplx), Xc, ld * sizeof(cplx), w16, (size_t)nc,
+                                        cudaMemcpyDeviceToHost, p->cs));
+        launch_theta_inplace(n, nc, Xc, ld, p->cs);
+        ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)(n + c0) * sink->ld2, sink->ld2 * sizeof(cplx), Xc, ld * sizeof(cplx), w16, (size_t)nc,
+                                        cudaMemcpyDeviceToHost, p->cs));
+        p->launches += 1;
       }
       c0 += nc;
     }
-    if (sink && !dist && p->cs) {               // the solver's stream continues (eigenvalues, status) after the last download
+    if (piped) {                                // the solver's stream continues (eigenvalues, status) after the last download
       ZQ_CUDA_CHECK(cudaEventRecord(p->ev_copy, p->cs));
       ZQ_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_copy, 0));
       cudaError_t e2 = cudaGetLastError();
@@ -1327,7 +1357,7 @@ int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, vo
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
   cudaEventRecord(a, st);
-  for (int i = 0; i < reps; ++i) launch_matvec_only(w, s, (quat*)y, st);
+  for (int i = 0; i < reps; ++i) launch_matvec_only(w, s, (quat*)y, st, false);   // K1 alone
   cudaEventRecord(b, st);
   ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
   float t = 0;

@@ -14,10 +14,15 @@
 // (v1 of this file reached 15-20 TFLOP/s) are freed.  A complex product is four real DMMAs on
 // (re, im) fragments; conjugation is a sign flip of the imaginary fragment in registers.
 //
-// Tiling: CTA tile BM x BN (64 x 128, 8 warps; or 64 x 64, 4 warps), warp tile 32 x 32, BK = 16,
-// 3-stage cp.async pipeline straight from global to (padded, bank-conflict-free) shared memory --
-// operands are stored interleaved complex exactly as in global memory, in whichever of the two
-// orientations (contiguous along the tile dimension, or contiguous along k) the caller's op needs.
+// Tiling (defaults; measured alternatives are listed where they are selected): the 4-product kernel k_zgemm_mma uses a
+// 64 x 64 CTA tile (4 warps, warp tile 32 x 32), the 3M kernel k_zgemm_3m a 64 x 32 CTA tile (4 warps, warp tile
+// 32 x 16, three accumulator sets); both BK = 8 with a 3-stage cp.async pipeline straight from global to (padded,
+// bank-conflict-free) shared memory -- operands are stored interleaved complex exactly as in global memory, in
+// whichever of the two orientations (contiguous along the tile dimension, or contiguous along k) the caller's op
+// needs.  The larger mma.sync .f64 shapes of the PTX ISA (m16n8k4/k8/k16) were checked: ptxas for sm_100a expands
+// each of them into DMMA.8x8x4 sequences (cuobjdump of tools/fp64_peak.cu: 1160 DMMA.8x8x4, no other DMMA shape), and
+// their fragment layout is the m8n8k4 layout repeated, so neither instruction count in SASS nor shared-memory loads
+// change -- m8n8k4 is the native FP64 tensor instruction of this chip.
 #include "kernels.h"
 
 namespace zq {
@@ -364,11 +369,10 @@ k_zgemm_3m(int M, int N, int K, cplx alpha, const cplx* __restrict__ A, size_t l
     }
 }
 
-template <int TA, int TB>
-void launch_3m(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
-               size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, SplitK sk,
-               cudaStream_t st) {
-  constexpr int BK = 8, STAGES = 3;
+template <int BK, int STAGES, int TA, int TB>
+void launch_3m_cfg(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
+                   size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, SplitK sk,
+                   cudaStream_t st) {
   using TileA = OpTile<64, TA == 1, BK>;
   using TileB = OpTile<32, TB == 0, BK>;
   const size_t smem = (size_t)STAGES * (TileA::ELEMS + TileB::ELEMS) * sizeof(cplx);
@@ -379,6 +383,19 @@ void launch_3m(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const
   dim3 g((M + 63) / 64, ncb >= 0 ? 2 * ncb : 2 * ((N + 63) / 64), batch);
   if (g.y == 0) return;
   k_zgemm_3m<BK, STAGES, TA, TB><<<g, 128, smem, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, sA, sB, sC, cb0, cbs, sk);
+}
+
+// ZQ_3M_CFG (development knob): pipeline shape of the 3M kernel -- 0 (default): BK 8 x 3 stages; 1: BK 16 x 2; 2: BK 8 x 4;
+// 3: BK 16 x 3 (2 CTAs per SM)
+template <int TA, int TB>
+void launch_3m(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B, size_t ldb, cplx beta, cplx* C,
+               size_t ldc, int lower, int batch, size_t sA, size_t sB, size_t sC, int cb0, int cbs, int ncb, SplitK sk,
+               cudaStream_t st) {
+  static const int cfg = [] { const char* e = getenv("ZQ_3M_CFG"); return e ? atoi(e) : 0; }();
+  if (cfg == 1) launch_3m_cfg<16, 2, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
+  else if (cfg == 2) launch_3m_cfg<8, 4, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
+  else if (cfg == 3) launch_3m_cfg<16, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
+  else launch_3m_cfg<8, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
 }
 
 template <int BM, int BN, int BK, int STAGES, int TA, int TB>
@@ -413,7 +430,7 @@ void launch_t(int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const 
   int cfg = cfg_env;
   if (ncb >= 0) cfg = 3;   // column-block addressing assumes BN = 64
   if (cfg == 0) {
-    cfg = 3;   // measured best on every shape of the solver (profiles/r01_gemm_configs.md)
+    cfg = 3;   // measured best on every shape of the solver (profiles/r01_gemm_cfg1.jsonl vs r01_gemm_cfg3.jsonl)
   }
   if (cfg == 1)
     launch_cfg<64, 128, 16, 3, TA, TB>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower, batch, sA, sB, sC, cb0, cbs, ncb, sk, st);
