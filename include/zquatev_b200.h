@@ -153,6 +153,12 @@ int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, vo
 int zq_test_zgemm(int ta, int tb, int M, int N, int K, const double* alpha, const void* A, long long lda,
                   const void* B, long long ldb, const double* beta, void* C, long long ldc, int lower, int reps,
                   double* ms);
+/* K4/K6 quaternion GEMM (eight real products per quaternion product): C = beta C + alpha op(A) op(B) with real alpha,
+ * beta; every operand is a pair of complex arrays, the b-part `*off` elements behind the a-part; ta/tb = 1: the
+ * operand is the quaternion conjugate transpose of the stored array.                                            */
+int zq_test_qgemm(int ta, int tb, int M, int N, int K, double alpha, const void* A, long long lda, long long aoff,
+                  const void* B, long long ldb, long long boff, double beta, void* C, long long ldc, long long coff,
+                  int lower, int reps, double* ms);
 /* selects the complex-product scheme of the NEXT zq_test_zgemm calls: 1 = 3M (three real products, used by the
  * solver for n >= 1024), 0 = conventional four products.  (A solve sets it again for itself.)              */
 void zq_test_set_gemm_3m(int on);

@@ -358,3 +358,64 @@ def solve(M, nb=8, tridiag_solver=None):
     out[:n, :n], out[n:, :n] = Xa, Xb
     out[:n, n:], out[n:, n:] = -c(Xb), c(Xa)
     return w, out
+
+
+# --------------------------------------------------------------------------------------
+# quaternion GEMM with eight real products (csrc/qgemm.cu restated)
+# --------------------------------------------------------------------------------------
+def q_components(Qa, Qb):
+    """(a, b) complex pair of a quaternion matrix Q = Qa + j Qb -> its four real component planes (1, i, j, k)."""
+    return [Qa.real.copy(), Qa.imag.copy(), Qb.real.copy(), -Qb.imag.copy()]
+
+
+def q_from_components(q):
+    return q[0] + 1j * q[1], q[2] - 1j * q[3]
+
+
+def q_conj_transpose(q):
+    """component planes of Q^H (quaternion conjugate transpose)"""
+    return [q[0].T, -q[1].T, -q[2].T, -q[3].T]
+
+
+def qgemm8(Aa, Ab, Ba, Bb):
+    """C = A B for quaternion matrices in complex-pair form with EIGHT real matrix products (bilinear rank of the
+    quaternion algebra; the products keep the a-combination on the left, so the identity holds for matrices):
+    exactly the combinations of csrc/qgemm.cu (combos_a / combos_b / epilogue).  Returns (Ca, Cb)."""
+    a1, a2, a3, a4 = q_components(Aa, Ab)
+    b1, b2, b3, b4 = q_components(Ba, Bb)
+    p1 = (a4 + a2) @ (b2 + b3)
+    p2 = (a1 - a3) @ (b1 + b4)
+    p3 = (a1 + a3) @ (b1 - b4)
+    p4 = (a4 - a2) @ (b2 - b3)
+    p5 = (a4 - a3) @ (b3 - b4)
+    p6 = (a2 + a1) @ (b2 + b1)
+    p7 = (a1 - a2) @ (b3 + b4)
+    p8 = (a4 + a3) @ (b1 - b2)
+    s123 = (p1 + p2) + p3
+    s = 0.5 * (s123 + p4)
+    return q_from_components([(s - p1) + p5, (s - s123) + p6, (s - p2) + p7, (s - p3) + p8])
+
+
+def qgemm_ref(Aa, Ab, Ba, Bb):
+    """the same product through the complex 2 x 2 block form Phi(A) (Ba; Bb) (what zgemm.cu's stacked GEMMs compute)"""
+    return Aa @ Ba - c(Ab) @ Bb, Ab @ Ba + c(Aa) @ Bb
+
+
+def backtransform_q8(D, E, tau, Xa, Xb, nb):
+    """K6 with the quaternion 8-product GEMMs: per panel Y = V^H X and X -= V (T Y) as quaternion products (T Y stays
+    a small stacked complex product, as in solver.cu)."""
+    n = D.shape[0]
+    Xa, Xb = Xa.copy(), Xb.copy()
+    for j0 in reversed(range(0, n - 1, nb)):
+        kb = min(nb, n - 1 - j0)
+        m = n - 1 - j0
+        P = phi_panel(D, E, j0, kb)
+        T = tfactor(P, tau[j0:j0 + kb])
+        Va, Vb = P[:m, :kb], P[m:, :kb]
+        VHa, VHb = c(Va).T, -Vb.T                         # quaternion conjugate transpose in pair form
+        Ya, Yb = qgemm8(VHa, VHb, Xa[j0 + 1:], Xb[j0 + 1:])
+        TY = T @ np.vstack([Ya, Yb])
+        Ua, Ub = qgemm8(Va, Vb, TY[:kb], TY[kb:])
+        Xa[j0 + 1:] -= Ua
+        Xb[j0 + 1:] -= Ub
+    return Xa, Xb

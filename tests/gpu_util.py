@@ -60,6 +60,21 @@ def zgemm(ta, tb, alpha, A, B, beta, C, lower=0, reps=0):
     return fhost(Cd, C.shape), ms.value
 
 
+def qgemm(ta, tb, alpha, Aa, Ab, Ba, Bb, beta, Ca, Cb, lower=0, reps=0):
+    """quaternion GEMM door: operands are (a, b) complex pairs AS STORED (before op); each pair is packed into one
+    column-major array with the b-part stacked below the a-part (b offset = number of rows of the a-part)."""
+    M, N = Ca.shape
+    K = Aa.shape[0] if ta else Aa.shape[1]
+    A = np.vstack([Aa, Ab]); B = np.vstack([Ba, Bb]); C = np.vstack([Ca, Cb])
+    Ad, Bd, Cd = fdev(A), fdev(B), fdev(C)
+    ms = ctypes.c_double(0)
+    rc = api.lib().zq_test_qgemm(ta, tb, M, N, K, float(alpha), Ad.data_ptr(), A.shape[0], Aa.shape[0], Bd.data_ptr(), B.shape[0], Ba.shape[0],
+                                 float(beta), Cd.data_ptr(), C.shape[0], M, lower, reps, ctypes.byref(ms))
+    assert rc == 0, rc
+    out = fhost(Cd, C.shape)
+    return out[:M], out[M:], ms.value
+
+
 def stedc(d, e):
     n = len(d)
     dd = dev(np.asarray(d, dtype=np.float64))

@@ -67,6 +67,35 @@ def test_zgemm(ta, tb, M, N, Kd, lower, three_m):
     assert np.max(np.abs(got - ref)) <= 1e-12 * Kd
 
 
+@pytest.mark.parametrize("ta,tb,M,N,Kd,lower", [(0, 1, 100, 100, 128, 1), (0, 1, 67, 67, 40, 1), (1, 0, 64, 130, 300, 0),
+                                                (0, 0, 200, 77, 64, 0), (0, 0, 5, 3, 2, 0), (1, 1, 33, 65, 17, 0),
+                                                (0, 0, 129, 129, 7, 0), (1, 0, 1, 1, 1, 0)])
+def test_qgemm8(ta, tb, M, N, Kd, lower):
+    """K4/K6 quaternion GEMM with eight real products (qgemm.cu) against the 2 x 2 complex block form and against
+    its numpy restatement (oracle.quat_kernels.qgemm8)."""
+    from tests import gpu_util as G
+    rng = np.random.default_rng(M * 11 + N + Kd)
+    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    sa = (Kd, M) if ta else (M, Kd)
+    sb = (N, Kd) if tb else (Kd, N)
+    Aa, Ab, Ba, Bb, Ca, Cb = cr(*sa), cr(*sa), cr(*sb), cr(*sb), cr(M, N), cr(M, N)
+    alpha, beta = -1.0, 1.0
+    ga, gb, _ = G.qgemm(ta, tb, alpha, Aa, Ab, Ba, Bb, beta, Ca, Cb, lower)
+    opA = (Aa.conj().T, -Ab.T) if ta else (Aa, Ab)          # quaternion conjugate transpose in pair form
+    opB = (Ba.conj().T, -Bb.T) if tb else (Ba, Bb)
+    ra, rb = K.qgemm_ref(opA[0], opA[1], opB[0], opB[1])
+    ra, rb = alpha * ra + beta * Ca, alpha * rb + beta * Cb
+    if lower:
+        mask = np.tril(np.ones((M, N), dtype=bool))
+        ra, rb = np.where(mask, ra, Ca), np.where(mask, rb, Cb)
+    assert np.max(np.abs(ga - ra)) <= 2e-12 * Kd and np.max(np.abs(gb - rb)) <= 2e-12 * Kd
+    fa, fb = K.qgemm8(opA[0], opA[1], opB[0], opB[1])       # same algorithm on the CPU: agreement to rounding of the sums
+    fa, fb = alpha * fa + beta * Ca, alpha * fb + beta * Cb
+    if lower:
+        fa, fb = np.where(mask, fa, Ca), np.where(mask, fb, Cb)
+    assert np.max(np.abs(ga - fa)) <= 2e-12 * Kd and np.max(np.abs(gb - fb)) <= 2e-12 * Kd
+
+
 @pytest.mark.parametrize("name,d,e", list(_tri_cases()))
 def test_k8_stedc_cases(name, d, e):
     from tests import gpu_util as G

@@ -181,3 +181,28 @@ def test_paired_backtransform_restatement(n, nb):
     a1, b1 = K.backtransform_paired(Df, Ef, tau, Xa.copy(), Xb.copy(), nb)
     scale = max(np.abs(a0).max(), np.abs(b0).max())
     assert np.abs(a0 - a1).max() <= 1e-13 * scale and np.abs(b0 - b1).max() <= 1e-13 * scale
+
+
+def test_qgemm8_restatement_and_backtransform():
+    """the eight-product quaternion GEMM (csrc/qgemm.cu restated in oracle.quat_kernels.qgemm8) equals the 2 x 2 complex
+    block product, and the back-transformation built on it keeps the quality of the stacked complex form"""
+    rng = np.random.default_rng(5)
+    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    Aa, Ab, Ba, Bb = cr(13, 9), cr(13, 9), cr(9, 11), cr(9, 11)
+    ra, rb = K.qgemm_ref(Aa, Ab, Ba, Bb)
+    fa, fb = K.qgemm8(Aa, Ab, Ba, Bb)
+    assert np.max(np.abs(ra - fa)) < 1e-13 and np.max(np.abs(rb - fb)) < 1e-13
+    n, nb = 150, 16
+    M = O.gen_sym(n, 9)
+    d, ala, alb, tau, Df, Ef = K.tridiagonalise(np.array(M[:n, :n]), np.array(M[n:, :n]), nb)
+    e, sa, sb = K.phase_chain(ala, alb)
+    w, Z = np.linalg.eigh(np.diag(d) + np.diag(e, -1) + np.diag(e, 1))
+    res = {}
+    for name, bt in (("stacked", K.backtransform), ("q8", K.backtransform_q8)):
+        Xa, Xb = bt(Df, Ef, tau, sa[:, None] * Z, sb[:, None] * Z, nb)
+        out = np.empty((2 * n, 2 * n), dtype=np.complex128)
+        out[:n, :n], out[n:, :n] = Xa, Xb
+        out[:n, n:], out[n:, n:] = -np.conj(Xb), np.conj(Xa)
+        res[name] = O.quality(M, out, w)
+    assert res["q8"][2] == 0.0
+    assert res["q8"][0] <= 1.5 * res["stacked"][0] + 0.01 and res["q8"][1] <= 1.5 * res["stacked"][1] + 0.05, res

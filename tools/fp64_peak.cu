@@ -59,6 +59,29 @@ __global__ void k_dmma16816(double* out, int iters) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA stream with R independent DADDs per DMMA interleaved: does the FP64 FMA pipe share issue / execution resources
+// with the FP64 tensor path?  (qgemm.cu forms its operand combinations with DADDs inside the main loop.)
+template <int R>
+__global__ void k_dmma_dadd(double* out, int iters) {
+  double c[8][2], s[8];
+  double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = i; c[i][1] = -i; s[i] = 0.5 * i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+#pragma unroll
+      for (int r = 0; r < R; ++r) asm volatile("add.f64 %0, %0, %1;" : "+d"(s[(i + r) & 7]) : "d"(a));
+    }
+  }
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += c[i][0] + c[i][1] + s[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
 template <class F>
 double timeit(F f, int reps) {
   cudaEvent_t a, b;
@@ -95,6 +118,18 @@ int main() {
       fl = 2.0 * 16 * 8 * 16 * 4 * iters * (double)grid * (tpb / 32);
       printf("{\"kernel\":\"dmma_m16n8k16\",\"tpb\":%d,\"ctas_per_sm\":%d,\"tflops\":%.2f}\n", tpb, bps, fl / ms * 1e-9);
     }
+  }
+  for (int bps : {1, 2}) {
+    const int tpb = 256, grid = sms * bps;
+    double fl = 2.0 * 8 * 8 * 4 * 8 * iters * (double)grid * (tpb / 32);
+    double ms = timeit([&] { k_dmma_dadd<0><<<grid, tpb>>>(out, iters); }, 5);
+    printf("{\"kernel\":\"dmma+0dadd\",\"ctas_per_sm\":%d,\"dmma_tflops\":%.2f}\n", bps, fl / ms * 1e-9);
+    ms = timeit([&] { k_dmma_dadd<1><<<grid, tpb>>>(out, iters); }, 5);
+    printf("{\"kernel\":\"dmma+1dadd\",\"ctas_per_sm\":%d,\"dmma_tflops\":%.2f}\n", bps, fl / ms * 1e-9);
+    ms = timeit([&] { k_dmma_dadd<2><<<grid, tpb>>>(out, iters); }, 5);
+    printf("{\"kernel\":\"dmma+2dadd\",\"ctas_per_sm\":%d,\"dmma_tflops\":%.2f}\n", bps, fl / ms * 1e-9);
+    ms = timeit([&] { k_dmma_dadd<4><<<grid, tpb>>>(out, iters); }, 5);
+    printf("{\"kernel\":\"dmma+4dadd\",\"ctas_per_sm\":%d,\"dmma_tflops\":%.2f}\n", bps, fl / ms * 1e-9);
   }
   printf("{\"sms\":%d,\"clock_khz\":%d,\"name\":\"%s\"}\n", sms, p.clockRate, p.name);
   return 0;

@@ -44,6 +44,7 @@ SYMBOLS = {
     "zq_test_matvec": (_I, [_I, _I, _P, _LL, _P, _P, _I, _P]),
     "zq_test_zgemm": (_I, [_I, _I, _I, _I, _I, _P, _P, _LL, _P, _LL, _P, _P, _LL, _I, _I, _P]),
     "zq_test_set_gemm_3m": (None, [_I]),
+    "zq_test_qgemm": (_I, [_I, _I, _I, _I, _I, _D, _P, _LL, _LL, _P, _LL, _LL, _D, _P, _LL, _LL, _I, _I, _P]),
     "zq_test_stedc": (_I, [_I, _P, _P, _P, _P]),
     "zq_test_bisect": (_I, [_I, _P, _P, _P]),
     "zq_test_tridiag": (_I, [_I, _I, _P, _LL, _P, _P, _P, _P]),

@@ -20,7 +20,7 @@ __host__ __device__ inline int dot_chunk_rows(int rows) {
   return r;
 }
 constexpr int K1_TPB_MAX = 8;      // column blocks per K1 CTA (a run); k1_tpb(m) picks 1, 2 or 4 from the trailing size
-int k1_tpb(int m);
+int k1_tpb(int m, int world);
 constexpr int ROWS_PER_CTA = 256;
 constexpr int PANEL_ROWS = 32;      // rows per CTA of the latency-bound panel kernels
 constexpr int MAX_NB_PANEL = 64;    // largest panel width
@@ -65,6 +65,8 @@ struct PanelWs {
                       //   v[r] = x[r] u1^{-1} (v[k+1] = 1): every consumer forms it on the fly.
   int xrec;           // index of the record (n on one GPU; the capacity of the landing buffer with the peer exchange)
   unsigned int* counter;   // CTA arrival counter of col_update's last-block epilogue (always left at 0)
+  const cplx* apanel; // multi-GPU: landing buffer of the current panel's columns [2 parts][MAX_NB_PANEL][apanel_ld]
+  size_t apanel_ld;   //   (null on one GPU: col_update reads column k from A)
   quat* p;            // [n] tau * (M v - corrections)
   quat* pd;           // [ceil(n/MV_TC)][n]  direct partial sums of K1
   quat* pt;           // [ceil(n/MV_TR)][n]  transposed partial sums of K1
@@ -91,9 +93,9 @@ struct PeerX {
   int rank, world;
   size_t nmax;                              // capacity (quaternions per vector)
   int rbmax;                                // row blocks (of PANEL_ROWS rows) per vector: flag capacity
-  quat* bx[PX_MAXW];                        // [g]: rank g's landing zone for x + record: [2 parities][nmax + 3]
+  cplx* apanel[PX_MAXW];                    // [g]: rank g's landing buffer for the current panel's columns: [2 parts][64][nmax]
   quat* ypart[PX_MAXW];                     // [g]: rank g's staging [2 parities][world][nmax]
-  unsigned long long* flags[PX_MAXW];       // [g]: rank g's flags: [0] x seq; [8 + ((parity*rbmax + rowblock)*PX_MAXW + src)] partial-y seq
+  unsigned long long* flags[PX_MAXW];       // [g]: rank g's flags: [0] panel seq; [8 + ((parity*rbmax + rowblock)*PX_MAXW + src)] partial-y seq
   int* info;                                // local status word (bit 8 = exchange timeout)
 };
 
@@ -104,10 +106,12 @@ void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
 // (2) after the all-reduce of w.p: corrections, tau scaling, partial Re(v^H p), unpack of the column
 void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st);
 void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st);
-// peer-exchange variants (seq = monotonically increasing sequence number of this column; w.x must point at the
-// landing buffer of this column's parity):
-//   owner: x rows + record pushed to every peer, then the flag;  others: finish w, last CTA waits for the flag
-void launch_col_update_px(const PanelWs& w, const PeerX& px, int k, int j0, bool owner, unsigned long long seq, cudaStream_t st);
+// multi-GPU, once per panel: the owner pushes rows [j0, n) of the panel's kb columns of D and E into every rank's landing
+// buffer and publishes seq (peer exchange); the others wait for it.  NCCL transport: pack into a local buffer instead.
+void launch_push_panel(const PanelWs& w, const PeerX& px, int j0, int kb, unsigned long long seq, cudaStream_t st);
+void launch_wait_panel(const PeerX& px, unsigned long long seq, cudaStream_t st);
+void launch_pack_panel(const PanelWs& w, cplx* buf, size_t ld, int j0, int kb, cudaStream_t st);
+// peer-exchange variant of reduce_correct (seq = monotonically increasing sequence number of this column):
 //   partial M v pushed per row block into every rank's staging slot + per-row-block flags, ordered sum, correction
 void launch_reduce_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st);
 void launch_finish_w(const PanelWs& w, int k_last, int j0, cudaStream_t st);
@@ -152,6 +156,18 @@ void zgemm_allow_3m(int on);
 void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx* A, size_t lda, const cplx* B,
                      size_t ldb, cplx beta, cplx* C, size_t ldc, int lower, int batch, size_t sA, size_t sB,
                      size_t sC, int cb0, int cbs, int ncb, cudaStream_t st);
+
+// K4/K6 quaternion GEMM with eight real products per quaternion product (qgemm.cu):  C = beta C + alpha op(A) op(B),
+// alpha and beta real.  A quaternion matrix is a pair of complex column-major arrays, the b-part `off` elements behind
+// the a-part.  ta/tb: 1 = the operand is the quaternion conjugate transpose of the stored array (stored K x M / N x K).
+// lower: only entries with row >= col.  Either `batch` independent products (strides sA, sB, sC) or split-K (sk != null,
+// sk->chunks pieces of sk->kc along K, piece z written to C + z sC; segA/segB unused).
+void launch_qgemm(int ta, int tb, int M, int N, int K, double alpha, const cplx* A, size_t lda, size_t aoff, const cplx* B,
+                  size_t ldb, size_t boff, double beta, cplx* C, size_t ldc, size_t coff, int lower, int batch, size_t sA,
+                  size_t sB, size_t sC, const SplitK* sk, cudaStream_t st, int cb0 = 0, int cbs = 1, int ncb = -1);
+// K4 operands of the quaternion form: Aq = [V W], Sq = [W V] (rows r0..n-1; each 2m x 2kb complex with the b-part
+// stacked below the a-part, ld 2m), so that  M[r0:, r0:] -= Aq Sq^H
+void launch_build_VW(const PanelWs& w, int r0, int kb, cplx* Aq, cplx* Sq, cudaStream_t st);
 
 // K6 helpers (backtransform.cu)
 //   P = Phi(V) of panel [j0, j0+kb): (2m x 2kb), ld 2m, m = n-1-j0 ; rows [0,m) <-> a-part rows j0+1..

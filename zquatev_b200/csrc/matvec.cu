@@ -218,10 +218,13 @@ __global__ void k_matvec_gather(int n, int s, int tpb, const quat* pd, const qua
 // m = 16384 / 8192 / 4096 is 0.83 / 0.81 / 0.67 with 1, 0.89 / 0.84 / 0.75 with 2, 0.93 / 0.85 / 0.75 with 4 blocks;
 // below m ~ 3500 the grid gets too small for runs).  ZQ_K1_TPB forces a value; ZQ_K1_TPB8 = trailing size from which 8
 // blocks are used.
-int k1_tpb(int m) {
+int k1_tpb(int m, int world) {
   static const int env = [] { const char* e = getenv("ZQ_K1_TPB"); return e ? atoi(e) : 0; }();
   static const int m8 = [] { const char* e = getenv("ZQ_K1_TPB8"); return e ? atoi(e) : 1 << 30; }();
   if (env > 0) return env < K1_TPB_MAX ? env : K1_TPB_MAX;
+  // with the column blocks dealt out to `world` ranks a launch holds 1/world of the tiles: the same number of CTAs as a
+  // single-GPU launch of trailing size m / sqrt(world)
+  if (world > 1) m = (int)((double)m / sqrt((double)world));
   if (m >= m8) return 8;
   return m >= 7168 ? 4 : (m >= 3584 ? 2 : 1);
 }
@@ -246,7 +249,7 @@ static void owned_runs(const PanelWs& w, int s, int tpb, int& R0, int& nR) {
 void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int s = k + 1, n = w.n;
   const int nI = (n - 1) / TR - s / TR + 1;
-  const int tpb = k1_tpb(n - s);
+  const int tpb = k1_tpb(n - s, w.world);
   int R0, nR;
   owned_runs(w, s, tpb, R0, nR);
   const int ncols = k - j0;
@@ -265,7 +268,7 @@ void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st, bool gather) {
   const int n = w.n;
   const int nI = (n - 1) / TR - s / TR + 1;
-  const int tpb = k1_tpb(n - s);
+  const int tpb = k1_tpb(n - s, 1);
   int R0, nR;
   owned_runs(w, s, tpb, R0, nR);
   // head = -1: no unit head row, v = x * record[2] for all rows >= s

@@ -13,15 +13,15 @@
 // All cross-CTA reductions go through small partial buffers summed in a fixed order, so the
 // result is bit-reproducible run to run.
 //
-// Multi-GPU (1-D block-cyclic columns, one process per GPU): the two per-column exchanges are fused
-// into these kernels over peer memory (CUDA IPC + NVLink stores, PeerX in kernels.h):
-//   * the owner's col_update pushes x (and its last CTA the scalar record) into every peer's landing
-//     buffer and publishes a sequence number; the last CTA of a non-owner's col_update waits for it,
-//     so K1 starts on data that is already there;
-//   * reduce_correct pushes its 32 rows of the local partial M v into slot [rank] of every rank,
-//     raises a per-row-block flag there, waits for the flags of the same row block from all ranks
-//     and sums the slots in rank order (bit-identical on every rank): no grid-wide barrier, no
-//     separate kernel, no NCCL call between the panel kernels.
+// Multi-GPU (1-D block-cyclic columns, one process per GPU).  ONE exchange per column and one per panel, both as
+// peer-memory stores issued by these kernels (CUDA IPC + NVLink, PeerX in kernels.h):
+//   * per panel: the owner of the panel's 64 columns pushes them (rows j0.., as they stand after the last trailing
+//     update) into every rank's landing buffer (push_panel); from there EVERY rank forms x, the reflector scalars and v
+//     of every column of the panel itself -- replicated, bit-identical work that was on the critical path of the
+//     owner anyway -- so no per-column broadcast of the reflector exists;
+//   * per column: reduce_correct pushes its 32 rows of the local partial M v into slot [rank] of every rank, raises a
+//     per-row-block flag there, waits for the flags of the same row block from all ranks and sums the slots in rank
+//     order (bit-identical on every rank): no grid-wide barrier, no separate kernel, no NCCL call.
 //
 // These kernels are latency-bound (n of each per solve): a CTA owns only PANEL_ROWS = 32 rows
 // (lane = row, coalesced column-major access) and its 8 warps split the inner loops over the
@@ -104,13 +104,10 @@ ZQ_D Refl make_reflector(double rest2, quat x1) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// col_update: rows r in [k, n).  ROLE 0: single GPU, or owner / everybody on the NCCL transport (x and the scalar
-// record stay local).  ROLE 1: owner with the peer exchange (x rows and the record are ALSO stored into every
-// peer's landing buffer, then the sequence number is published).  ROLE 2: non-owner with the peer exchange (only
-// finishes w of column k-1; its last CTA waits until the owner's x and record have landed).
+// col_update: rows r in [k, n).  Column k of the matrix as of the start of the panel is read from A or, on several
+// GPUs, from the panel landing buffer w.apanel (only the owner's copy of A is current).
 // ---------------------------------------------------------------------------------------------
-template <int ROLE>
-__global__ void __launch_bounds__(NT) k_col_update(PanelWs w, PeerX px, int k, int j0, int ng_parts, unsigned long long seq) {
+__global__ void __launch_bounds__(NT) k_col_update(PanelWs w, int k, int j0, int ng_parts) {
   pdl_enter();
   const int n = w.n, i = k - j0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -120,7 +117,6 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, PeerX px, int k, i
   __shared__ double s_red[32];
   __shared__ int s_last;
   const bool act = r < n;
-  const size_t xpar = (ROLE != 0) ? (size_t)(k & 1) * (px.nmax + 3) : 0;   // landing buffers alternate by column parity
 
   quat wr = qzero();       // W(r, i-1) for this thread's row
   if (i > 0) {
@@ -138,63 +134,63 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, PeerX px, int k, i
         pan_ptr(w, 3, i - 1)[r] = wr.b;
       }
     }
-    if (ROLE != 2) {
-      // row-k coefficients: qconj(W(k,t)), qconj(V(k,t)), t < i
-      for (int t = threadIdx.x; t < i; t += NT) {
-        quat wk, vk;
-        if (t == i - 1) {
-          quat pk = w.p[k];
-          quat vkk = qmake(va[k], vb[k]);
-          wk = qmake(csub(pk.a, cscale(vkk.a, coef)), csub(pk.b, cscale(vkk.b, coef)));
-          vk = vkk;
-        } else {
-          wk = qmake(pan_ptr(w, 2, t)[k], pan_ptr(w, 3, t)[k]);
-          vk = qmake(pan_ptr(w, 0, t)[k], pan_ptr(w, 1, t)[k]);
-        }
-        qW[t] = qconj(wk);
-        qV[t] = qconj(vk);
+    // row-k coefficients: qconj(W(k,t)), qconj(V(k,t)), t < i
+    for (int t = threadIdx.x; t < i; t += NT) {
+      quat wk, vk;
+      if (t == i - 1) {
+        quat pk = w.p[k];
+        quat vkk = qmake(va[k], vb[k]);
+        wk = qmake(csub(pk.a, cscale(vkk.a, coef)), csub(pk.b, cscale(vkk.b, coef)));
+        vk = vkk;
+      } else {
+        wk = qmake(pan_ptr(w, 2, t)[k], pan_ptr(w, 3, t)[k]);
+        vk = qmake(pan_ptr(w, 0, t)[k], pan_ptr(w, 1, t)[k]);
       }
+      qW[t] = qconj(wk);
+      qV[t] = qconj(vk);
     }
   }
   __syncthreads();
 
-  if (ROLE != 2) {
-    quat part = qzero();     // - sum over this warp's panel columns
-    quat acol = qzero();     // A(r, k): issued before the panel loop so its HBM latency hides behind it
-    if (warp == 0 && act) acol = qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]);
-    if (act) {
+  quat part = qzero();     // - sum over this warp's panel columns
+  quat acol = qzero();     // A(r, k): issued before the panel loop so its HBM latency hides behind it
+  if (warp == 0 && act) {
+    if (w.apanel) {        // landing buffer [part][panel column][row], written by the panel's owner over NVLink: read at L2
+      const double2* pa = reinterpret_cast<const double2*>(w.apanel + (size_t)i * w.apanel_ld + r);
+      const double2* pb = reinterpret_cast<const double2*>(w.apanel + ((size_t)MAX_NB_PANEL + i) * w.apanel_ld + r);
+      acol = qmake(__ldcg(pa), __ldcg(pb));
+    } else {
+      acol = qmake(w.A[(size_t)r + (size_t)k * w.lda], w.A[(size_t)(n + r) + (size_t)k * w.lda]);
+    }
+  }
+  if (act) {
 #pragma unroll 4
-      for (int t = warp; t < i; t += NW) {
-        quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
-        quat wrt = (t == i - 1) ? wr : qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
-        qfms(part, vrt, qW[t]);
-        qfms(part, wrt, qV[t]);
-      }
+    for (int t = warp; t < i; t += NW) {
+      quat vrt = qmake(pan_ptr(w, 0, t)[r], pan_ptr(w, 1, t)[r]);
+      quat wrt = (t == i - 1) ? wr : qmake(pan_ptr(w, 2, t)[r], pan_ptr(w, 3, t)[r]);
+      qfms(part, vrt, qW[t]);
+      qfms(part, wrt, qV[t]);
     }
-    quat col = warps_sum(part, red, warp, lane);
-    double nr = 0.0;
-    if (warp == 0 && act) {
-      col = qadd(col, acol);
-      if (r == k) {
-        w.d[k] = col.a.x;
-      } else {
-        w.x[r] = col;
-        if (ROLE == 1) {
-          for (int g = 0; g < px.world; ++g)
-            if (g != px.rank) px.bx[g][xpar + r] = col;                 // NVLink peer store
-        }
-        if (r >= k + 2) nr = qnorm2(col);
-      }
+  }
+  quat col = warps_sum(part, red, warp, lane);
+  double nr = 0.0;
+  if (warp == 0 && act) {
+    col = qadd(col, acol);
+    if (r == k) {
+      w.d[k] = col.a.x;
+    } else {
+      w.x[r] = col;
+      if (r >= k + 2) nr = qnorm2(col);
     }
-    if (warp == 0) {
-      nr = warp_sum(nr);
-      if (lane == 0) w.nrm_part[blockIdx.x] = nr;
-    }
+  }
+  if (warp == 0) {
+    nr = warp_sum(nr);
+    if (lane == 0) w.nrm_part[blockIdx.x] = nr;
   }
   if (k + 1 >= n) return;                         // last diagonal entry only: no reflector
 
-  // ---- the last CTA to arrive closes the column ----
-  if (ROLE == 1) __threadfence_system(); else __threadfence();
+  // ---- the last CTA to arrive closes the column: reflector scalars -> record ----
+  __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned prev = atomicAdd(w.counter, 1u);
@@ -204,31 +200,62 @@ __global__ void __launch_bounds__(NT) k_col_update(PanelWs w, PeerX px, int k, i
   if (!s_last) return;
   if (threadIdx.x == 0) *(volatile unsigned int*)w.counter = 0u;
   __threadfence();
-  if (ROLE == 2) {
-    // the owner's x and scalar record for this column must have landed before K1 (next in the stream) reads them
-    if (threadIdx.x == 0) px_wait(px.flags[px.rank] + 0, seq, px.info);
-    return;
-  }
   const double rest2 = sum_parts_cg(w.nrm_part, gridDim.x, s_red);
   if (threadIdx.x == 0) {
     const double2* xp = reinterpret_cast<const double2*>(w.x + k + 1);
     const quat x1 = qmake(__ldcg(xp), __ldcg(xp + 1));
     const Refl f = make_reflector(rest2, x1);
-    const quat sc = qmake(cmake(__ldcg(w.d + k), f.nx), cmake(f.tau, 0.0));
-    w.x[w.xrec] = sc;
+    w.x[w.xrec] = qmake(cmake(__ldcg(w.d + k), f.nx), cmake(f.tau, 0.0));
     w.x[w.xrec + 1] = f.alpha;
     w.x[w.xrec + 2] = f.inv;
-    if (ROLE == 1) {
-      for (int g = 0; g < px.world; ++g)
-        if (g != px.rank) {
-          quat* rec = px.bx[g] + xpar + px.nmax;
-          rec[0] = sc; rec[1] = f.alpha; rec[2] = f.inv;
-        }
-      __threadfence_system();
-      for (int g = 0; g < px.world; ++g)
-        if (g != px.rank) st_relaxed_sys(px.flags[g] + 0, seq);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// push_panel (multi-GPU, once per panel, owner only): rows [j0, n) of the panel's kb columns of D and E -> the landing
+// buffer of EVERY rank (own included), then the sequence number -> the peers' panel flag.
+// wait_flag (the other ranks): one thread waits until the flag has arrived.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) k_push_panel(PanelWs w, PeerX px, int j0, int kb, unsigned long long seq) {
+  const int n = w.n, t = blockIdx.y;
+  const int r = j0 + blockIdx.x * NT + threadIdx.x;
+  __shared__ int s_last;
+  if (r < n) {
+    const cplx d = w.A[(size_t)r + (size_t)(j0 + t) * w.lda];
+    const cplx e = w.A[(size_t)(n + r) + (size_t)(j0 + t) * w.lda];
+    const size_t ia = (size_t)t * px.nmax + r, ib = ((size_t)MAX_NB_PANEL + t) * px.nmax + r;
+    for (int g = 0; g < px.world; ++g) {
+      px.apanel[g][ia] = d;
+      px.apanel[g][ib] = e;
     }
   }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(w.counter, 1u);
+    s_last = (prev == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x == 0) {
+    *(volatile unsigned int*)w.counter = 0u;
+    __threadfence_system();
+    for (int g = 0; g < px.world; ++g)
+      if (g != px.rank) st_relaxed_sys(px.flags[g] + 0, seq);
+  }
+}
+
+__global__ void k_wait_flag(PeerX px, int idx, unsigned long long seq) {
+  if (threadIdx.x == 0) px_wait(px.flags[px.rank] + idx, seq, px.info);
+}
+
+// local variant for the NCCL transport: the owner packs the panel's columns into its OWN buffer (then ncclBroadcast)
+__global__ void __launch_bounds__(NT) k_pack_panel(PanelWs w, cplx* buf, size_t ld, int j0) {
+  const int n = w.n, t = blockIdx.y;
+  const int r = j0 + blockIdx.x * NT + threadIdx.x;
+  if (r >= n) return;
+  buf[(size_t)t * ld + r] = w.A[(size_t)r + (size_t)(j0 + t) * w.lda];
+  buf[((size_t)MAX_NB_PANEL + t) * ld + r] = w.A[(size_t)(n + r) + (size_t)(j0 + t) * w.lda];
 }
 
 // v[r] of the current column from x and the scalar record (read at L2: they may have been written by a peer GPU
@@ -404,6 +431,22 @@ __global__ void __launch_bounds__(256) k_build_LR(PanelWs w, int r0, int kb, cpl
   R[rr + (size_t)(3 * kb + t) * ldr] = cconj(vb);
 }
 
+// quaternion form of the K4 operands (qgemm.cu): Aq = [V W], Sq = [W V], a-part rows [0, m), b-part rows [m, 2m)
+__global__ void __launch_bounds__(256) k_build_VW(PanelWs w, int r0, int kb, cplx* Aq, cplx* Sq) {
+  const int n = w.n, m = n - r0;
+  const int t = blockIdx.y;
+  const int rr = blockIdx.x * 256 + threadIdx.x;
+  if (rr >= m) return;
+  const int r = r0 + rr;
+  const cplx va = pan_ptr(w, 0, t)[r], vb = pan_ptr(w, 1, t)[r];
+  const cplx wa = pan_ptr(w, 2, t)[r], wb = pan_ptr(w, 3, t)[r];
+  const size_t ld = 2 * (size_t)m;
+  Aq[rr + (size_t)t * ld] = va;          Aq[m + rr + (size_t)t * ld] = vb;
+  Aq[rr + (size_t)(kb + t) * ld] = wa;   Aq[m + rr + (size_t)(kb + t) * ld] = wb;
+  Sq[rr + (size_t)t * ld] = wa;          Sq[m + rr + (size_t)t * ld] = wb;
+  Sq[rr + (size_t)(kb + t) * ld] = va;   Sq[m + rr + (size_t)(kb + t) * ld] = vb;
+}
+
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace
@@ -411,25 +454,28 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 void launch_col_update(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k;                    // rows k..n-1
   const int ng = (k > j0) ? cdiv(w.n - k, PR) : 0;   // g_part written by reduce_correct of column k-1 (rows k..n-1)
-  launch_chain(k_col_update<0>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, ng, 0ull);
+  launch_chain(k_col_update, dim3(cdiv(rows, PR)), dim3(NT), st, w, k, j0, ng);
 }
 
-void launch_col_update_px(const PanelWs& w, const PeerX& px, int k, int j0, bool owner, unsigned long long seq, cudaStream_t st) {
-  const int rows = w.n - k;
-  const int ng = (k > j0) ? cdiv(w.n - k, PR) : 0;
-  if (owner) launch_chain(k_col_update<1>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, ng, seq);
-  else       launch_chain(k_col_update<2>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, ng, seq);
+void launch_push_panel(const PanelWs& w, const PeerX& px, int j0, int kb, unsigned long long seq, cudaStream_t st) {
+  k_push_panel<<<dim3(cdiv(w.n - j0, NT), kb), NT, 0, st>>>(w, px, j0, kb, seq);
+}
+
+void launch_wait_panel(const PeerX& px, unsigned long long seq, cudaStream_t st) { k_wait_flag<<<1, 32, 0, st>>>(px, 0, seq); }
+
+void launch_pack_panel(const PanelWs& w, cplx* buf, size_t ld, int j0, int kb, cudaStream_t st) {
+  k_pack_panel<<<dim3(cdiv(w.n - j0, NT), kb), NT, 0, st>>>(w, buf, ld, j0);
 }
 
 void launch_reduce_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   const int nch = cdiv(rows, dot_chunk_rows(rows));
-  launch_chain(k_reduce_correct<0>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, k1_tpb(rows), 0ull);
+  launch_chain(k_reduce_correct<0>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, j0, nch, k1_tpb(rows, w.world), 0ull);
 }
 
 void launch_reduce_partial(const PanelWs& w, int k, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  launch_chain(k_reduce_correct<1>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, k, 0, k1_tpb(rows), 0ull);
+  launch_chain(k_reduce_correct<1>, dim3(cdiv(rows, PR)), dim3(NT), st, w, PeerX{}, k, k, 0, k1_tpb(rows, w.world), 0ull);
 }
 
 void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
@@ -440,12 +486,18 @@ void launch_correct(const PanelWs& w, int k, int j0, cudaStream_t st) {
 
 void launch_reduce_correct_px(const PanelWs& w, const PeerX& px, int k, int j0, unsigned long long seq, cudaStream_t st) {
   const int rows = w.n - k - 1;
-  launch_chain(k_reduce_correct<3>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, cdiv(rows, dot_chunk_rows(rows)), k1_tpb(rows), seq);
+  launch_chain(k_reduce_correct<3>, dim3(cdiv(rows, PR)), dim3(NT), st, w, px, k, j0, cdiv(rows, dot_chunk_rows(rows)), k1_tpb(rows, w.world), seq);
 }
 
 void launch_finish_w(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rows = w.n - k - 1;
   launch_chain(k_finish_w, dim3(cdiv(rows, NT)), dim3(NT), st, w, k, j0, cdiv(rows, PR));
+}
+
+void launch_build_VW(const PanelWs& w, int r0, int kb, cplx* Aq, cplx* Sq, cudaStream_t st) {
+  const int m = w.n - r0;
+  dim3 g(cdiv(m, 256), kb);
+  k_build_VW<<<g, 256, 0, st>>>(w, r0, kb, Aq, Sq);
 }
 
 void launch_build_LR(const PanelWs& w, int r0, int kb, cplx* L, cplx* R, cudaStream_t st) {

@@ -47,6 +47,7 @@ struct Plan {
   int* info_dev = nullptr;
   DcWs* dc = nullptr;
   cplx* Dfull = nullptr;     // host-pointer mode staging, 2n x 2n
+  cplx* apanel = nullptr;    // multi-GPU over the NCCL transport: the current panel's columns [2][64][n] (allocated on first use)
   double* eig_dev = nullptr;
   cudaEvent_t ev[6] = {};
   cudaEvent_t ev_gather = nullptr;   // multi-GPU: recorded before the NCCL gather of the eigenvector shards
@@ -125,6 +126,7 @@ static void plan_free(Plan* p) {
   if (!p) return;
   if (p->slab) cudaFree(p->slab);
   if (p->Dfull) cudaFree(p->Dfull);
+  if (p->apanel) cudaFree(p->apanel);
   if (p->dc) dc_destroy(p->dc);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->ev_gather) cudaEventDestroy(p->ev_gather);
@@ -138,6 +140,13 @@ static void plan_free(Plan* p) {
 }
 
 static int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// K4/K6 as quaternion GEMMs with eight real products (qgemm.cu) instead of stacked complex 3M GEMMs: where the 3M scheme
+// is allowed (n >= 1024); ZQ_QGEMM=0 keeps the stacked complex form.
+static bool use_qgemm(int n) {
+  static const int on = [] { const char* e = getenv("ZQ_QGEMM"); return e ? atoi(e) : 1; }();
+  return on && n >= 1024;
+}
 
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("ZQ_PDL"); return e ? atoi(e) != 0 : true; }();
@@ -194,7 +203,7 @@ static int plan_create(int n, int nb, Plan** out) {
   if (e != cudaSuccess) { delete p; return zq_cuda_fail(e, __FILE__, __LINE__); }
   char* b = p->slab;
   PanelWs& w = p->pw;
-  w.n = n; w.nb = nb; w.lda = 0; w.A = nullptr; w.rank = 0; w.world = 1;
+  w.n = n; w.nb = nb; w.lda = 0; w.A = nullptr; w.rank = 0; w.world = 1; w.apanel = nullptr; w.apanel_ld = 0;
   w.pan = (cplx*)(b + o.pan); w.x = (quat*)(b + o.x); w.xrec = n; w.counter = (unsigned int*)(b + o.cnt); w.p = (quat*)(b + o.p);
   w.pd = (quat*)(b + o.pd); w.pt = (quat*)(b + o.pt); w.dotW = (quat*)(b + o.dW); w.dotV = (quat*)(b + o.dV);
   w.nrm_part = (double*)(b + o.np); w.g_part = (double*)(b + o.gp);
@@ -343,11 +352,19 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
     launch_finish_w(w, j0 + kb - 1, j0, st);
     const int r0 = j0 + kb, m = n - r0;
     if (m > 0) {
-      launch_build_LR(w, r0, kb, p->L, p->R, st);
-      if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
-      // [D;E][r0:, r0:] -= L R^H on the lower triangles: batch 0 = D block, batch 1 = E block
-      launch_zgemm(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
-                   w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, st);
+      if (use_qgemm(n)) {
+        // (D + jE)[r0:, r0:] -= [V W] [W V]^H as ONE quaternion product, lower triangles
+        launch_build_VW(w, r0, kb, p->L, p->R, st);
+        if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
+        launch_qgemm(0, 1, m, m, 2 * kb, -1.0, p->L, 2 * (size_t)m, (size_t)m, p->R, 2 * (size_t)m, (size_t)m, 1.0,
+                     w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, (size_t)n, 1, 1, 0, 0, 0, nullptr, st);
+      } else {
+        launch_build_LR(w, r0, kb, p->L, p->R, st);
+        if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
+        // [D;E][r0:, r0:] -= L R^H on the lower triangles: batch 0 = D block, batch 1 = E block
+        launch_zgemm(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
+                     w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, st);
+      }
       if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb) + 1], st);
       p->launches += 3;
     }
@@ -357,16 +374,16 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
   if (n >= 2048) l2_window(st, w.pan, 0);
 }
 
-// Exchange-buffer layout per rank: [bx: 2 parities x (nmax+3) quats][ypart: 2*PX_MAXW*nmax quats][flags: 8 + 2*rbmax*PX_MAXW u64]
+// Exchange-buffer layout per rank: [apanel: 2 x 64 x nmax complex][ypart: 2*PX_MAXW*nmax quats][flags: 8 + 2*rbmax*PX_MAXW u64]
 static int px_rbmax(size_t nmax) { return (int)((nmax + PANEL_ROWS - 1) / PANEL_ROWS) + 1; }
 static size_t px_bytes(size_t nmax) {
-  return (2 * (nmax + 3) + 2 * (size_t)PX_MAXW * nmax) * sizeof(quat) + (8 + 2 * (size_t)px_rbmax(nmax) * PX_MAXW) * 8;
+  return (size_t)2 * MAX_NB_PANEL * nmax * sizeof(cplx) + 2 * (size_t)PX_MAXW * nmax * sizeof(quat) + (8 + 2 * (size_t)px_rbmax(nmax) * PX_MAXW) * 8;
 }
 
 static void px_fill(PeerX& px, int g, char* base, size_t nmax) {
-  px.bx[g] = (quat*)base;
-  px.ypart[g] = (quat*)base + 2 * (nmax + 3);
-  px.flags[g] = (unsigned long long*)((quat*)base + 2 * (nmax + 3) + 2 * (size_t)PX_MAXW * nmax);
+  px.apanel[g] = (cplx*)base;
+  px.ypart[g] = (quat*)(px.apanel[g] + (size_t)2 * MAX_NB_PANEL * nmax);
+  px.flags[g] = (unsigned long long*)(px.ypart[g] + 2 * (size_t)PX_MAXW * nmax);
 }
 
 static void px_teardown() {
@@ -448,66 +465,83 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
     p->k4ev.resize(2 * (size_t)(n / nb + 1));
     for (size_t i = old; i < p->k4ev.size(); ++i) cudaEventCreate(&p->k4ev[i]);
   }
-  quat* const x_local = w.x;
   w.rank = g_rank;
   w.world = G;
   struct Restore {              // the cached plan must never keep the distributed geometry, whatever the exit path
-    PanelWs& w; quat* x; int n;
-    ~Restore() { w.rank = 0; w.world = 1; w.x = x; w.xrec = n; }
-  } restore{w, x_local, n};
+    PanelWs& w;
+    ~Restore() { w.rank = 0; w.world = 1; w.apanel = nullptr; w.apanel_ld = 0; }
+  } restore{w};
   const bool use_px = g_px.world == G && (size_t)n <= g_px.nmax;
   if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
   PeerX px = g_px;
   px.info = p->info_dev;
+  if (use_px) {
+    w.apanel = px.apanel[g_rank];
+    w.apanel_ld = px.nmax;
+  } else {
+    if (!p->apanel) ZQ_CUDA_CHECK(cudaMalloc(&p->apanel, (size_t)2 * MAX_NB_PANEL * n * sizeof(cplx)));
+    w.apanel = p->apanel;
+    w.apanel_ld = (size_t)n;
+  }
   cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
   for (int j0 = 0; j0 < n - 1; j0 += nb) {
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
     const int owner = (j0 / nb) % G;
+    // the panel's columns (current only on their owner) go to every rank once; everything per column that depends on
+    // them -- x, the reflector scalars, v -- is then formed by every rank itself
+    if (use_px) {
+      const unsigned long long pseq = g_seq_base + (unsigned long long)j0 + 1ull;
+      if (owner == g_rank) launch_push_panel(w, px, j0, kb, pseq, st);
+      else launch_wait_panel(px, pseq, st);
+    } else {
+      if (owner == g_rank) launch_pack_panel(w, p->apanel, (size_t)n, j0, kb, st);
+      ZQ_NCCL_CHECK(g_nccl.Broadcast(p->apanel, p->apanel, (size_t)2 * (2 * MAX_NB_PANEL) * n, ncclDouble, owner, g_comm, st));
+    }
+    p->launches += 1;
     for (int i = 0; i < kb; ++i) {
       const int k = j0 + i, m = n - k - 1;
+      launch_col_update(w, k, j0, st);
+      if (prof) cudaEventRecord(p->k1ev[2 * k], st);
+      launch_matvec(w, k, j0, st);
+      if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
       if (use_px) {
-        // x and the record of column k live in this rank's landing buffer of parity k & 1 (owner: written locally)
         const unsigned long long seq = g_seq_base + (unsigned long long)k + 1ull;
-        w.x = px.bx[g_rank] + (size_t)(k & 1) * (px.nmax + 3);
-        w.xrec = (int)px.nmax;
-        launch_col_update_px(w, px, k, j0, owner == g_rank, seq, st);
-        if (prof) cudaEventRecord(p->k1ev[2 * k], st);
-        launch_matvec(w, k, j0, st);
-        if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
         launch_reduce_correct_px(w, px, k, j0, seq, st);
         p->launches += 3;
       } else {
-        launch_col_update(w, k, j0, st);           // non-owners: finishes w; their x is overwritten by the broadcast
-        ZQ_NCCL_CHECK(g_nccl.Broadcast(w.x + k + 1, w.x + k + 1, (size_t)4 * (m + 3), ncclDouble, owner, g_comm, st));
-        if (prof) cudaEventRecord(p->k1ev[2 * k], st);
-        launch_matvec(w, k, j0, st);
-        if (prof) cudaEventRecord(p->k1ev[2 * k + 1], st);
         launch_reduce_partial(w, k, st);
         ZQ_NCCL_CHECK(g_nccl.AllReduce(w.p + k + 1, w.p + k + 1, (size_t)4 * m, ncclDouble, ncclSum, g_comm, st));
         launch_correct(w, k, j0, st);
-        p->launches += 6;
+        p->launches += 5;
       }
     }
     launch_finish_w(w, j0 + kb - 1, j0, st);
     const int r0 = j0 + kb, m = n - r0;
     if (m > 0) {
-      launch_build_LR(w, r0, kb, p->L, p->R, st);
       // owned 64-column blocks of the trailing matrix: global block (r0/64 + jt), jt = cb0, cb0 + G, ...
       const int b0 = r0 / MV_TC, nblk = (m + MV_TC - 1) / MV_TC;
       const int cb0 = ((g_rank - b0 % G) + G) % G;
       const int ncb = cb0 >= nblk ? 0 : (nblk - 1 - cb0) / G + 1;
-      if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
-      launch_zgemm_cb(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
-                      w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, cb0, G, ncb, st);
+      if (use_qgemm(n)) {
+        launch_build_VW(w, r0, kb, p->L, p->R, st);
+        if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
+        launch_qgemm(0, 1, m, m, 2 * kb, -1.0, p->L, 2 * (size_t)m, (size_t)m, p->R, 2 * (size_t)m, (size_t)m, 1.0,
+                     w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, (size_t)n, 1, 1, 0, 0, 0, nullptr, st, cb0, G, ncb);
+      } else {
+        launch_build_LR(w, r0, kb, p->L, p->R, st);
+        if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
+        launch_zgemm_cb(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
+                        w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, cb0, G, ncb, st);
+      }
       if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb) + 1], st);
       p->launches += 3;
     }
   }
-  w.x = x_local;
-  w.xrec = n;
-  launch_col_update(w, n - 1, n - 1, st);          // d[n-1]: valid on the owner of the last column block
+  // d[n-1]: the last diagonal entry is current on the owner of the last column block only
+  w.apanel = nullptr;
+  launch_col_update(w, n - 1, n - 1, st);
   ZQ_NCCL_CHECK(g_nccl.Broadcast(w.d + n - 1, w.d + n - 1, 1, ncclDouble, ((n - 1) / nb) % G, g_comm, st));
   p->launches += 1;
   if (use_px) g_seq_base += (unsigned long long)n + 8ull;
@@ -596,6 +630,30 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
     const size_t ldp = 2 * (size_t)m;
     cplx* Xa = X + (size_t)(j0 + 1);
     cplx* Xb = X + (size_t)(n + j0 + 1);
+    if (use_qgemm(n)) {
+      // quaternion form: V = (Va; Vb) is the first kb columns of P.  Y = V^H X (split-K over the m rows, parts summed in a
+      // fixed order), TY = T Y (small, stacked complex), X -= V TY
+      const size_t ypart = (size_t)2 * kb * ncols;
+      const int ctas1 = ((kb + 31) / 32) * ((ncols + 31) / 32);
+      int chunks = (8 * 296 + ctas1 - 1) / ctas1;                      // aim at >= 8 waves of 2 CTAs x 148 SMs
+      const int cap_mem = (int)(p->yp_elems / ypart), cap_k = m / 256;
+      if (chunks > cap_mem) chunks = cap_mem;
+      if (chunks > 2 * YP_MAX_CHUNKS) chunks = 2 * YP_MAX_CHUNKS;
+      if (chunks > cap_k) chunks = cap_k;
+      if (chunks < 1) chunks = 1;
+      SplitK sk;
+      sk.kc = (((m + chunks - 1) / chunks) + 7) & ~7;
+      sk.chunks = (m + sk.kc - 1) / sk.kc;
+      launch_qgemm(1, 0, kb, ncols, m, 1.0, p->P, ldp, (size_t)m, Xa, ldx, (size_t)n, 0.0, p->YP, 2 * (size_t)kb, (size_t)kb, 0, 1, 0, 0,
+                   ypart, &sk, st);
+      launch_sum_parts(ypart, sk.chunks, p->YP, ypart, p->Y, st);
+      launch_zgemm(0, 0, 2 * kb, ncols, 2 * kb, cmake(1, 0), p->T + (size_t)(j0 / nb) * 4 * nb * nb, 2 * (size_t)kb, p->Y, 2 * (size_t)kb, cmake(0, 0),
+                   p->TY, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
+      launch_qgemm(0, 0, m, ncols, kb, -1.0, p->P, ldp, (size_t)m, p->TY, 2 * (size_t)kb, (size_t)kb, 1.0, Xa, ldx, (size_t)n, 0, 1, 0, 0, 0,
+                   nullptr, st);
+      p->launches += 5;
+      continue;
+    }
     // Y = P^H X.  K runs over two segments (a-rows, b-rows of P and X); its 2kb x ncols output alone gives
     // 2 x ncols/32 CTAs (1024 at ncols = 16384: 2.3 waves; 128 on an 8-GPU column shard: under one wave), so the
     // segments are cut into K-chunks that run as one launch and are summed in a fixed order.
@@ -1393,6 +1451,30 @@ int zq_test_zgemm(int ta, int tb, int M, int N, int K, const double* alpha, cons
 }
 
 void zq_test_set_gemm_3m(int on) { zgemm_allow_3m(on); }
+
+int zq_test_qgemm(int ta, int tb, int M, int N, int K, double alpha, const void* A, long long lda, long long aoff, const void* B,
+                  long long ldb, long long boff, double beta, void* C, long long ldc, long long coff, int lower, int reps, double* ms) {
+  cudaStream_t st = 0;
+  launch_qgemm(ta, tb, M, N, K, alpha, (const cplx*)A, (size_t)lda, (size_t)aoff, (const cplx*)B, (size_t)ldb, (size_t)boff, beta, (cplx*)C,
+               (size_t)ldc, (size_t)coff, lower, 1, 0, 0, 0, nullptr, st);
+  if (reps > 0) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    for (int i = 0; i < reps; ++i)
+      launch_qgemm(ta, tb, M, N, K, alpha, (const cplx*)A, (size_t)lda, (size_t)aoff, (const cplx*)B, (size_t)ldb, (size_t)boff, beta,
+                   (cplx*)C, (size_t)ldc, (size_t)coff, lower, 1, 0, 0, 0, nullptr, st);
+    cudaEventRecord(b, st);
+    ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+    float t = 0;
+    cudaEventElapsedTime(&t, a, b);
+    if (ms) *ms = t / reps;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+  }
+  ZQ_CUDA_CHECK(cudaStreamSynchronize(st));
+  ZQ_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 int zq_test_stedc(int n, const double* d, const double* e, double* w, double* Z) {
   cudaStream_t st = 0;
