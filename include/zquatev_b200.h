@@ -96,6 +96,23 @@ int zquatev_b200_workspace_query(int n2, const zq_options* opt, unsigned long lo
 /* phase timings of the handle's last solve (layout of zquatev_b200_last_phases)                              */
 int zquatev_b200_handle_phases(zq_handle_t handle, double ms[8]);
 
+/* ---- the steps either side of the solver in the caller ----------------------------------------
+ * Products of quaternion-structured matrices Phi(Q) = ( Qa  -conj Qb ; Qb  conj Qa ) on the device, on the kernel the
+ * solver's own K4 / K6 use (eight real products per quaternion product, qgemm.cu).  Every matrix is passed as its
+ * LEFT half, a-part rows [0, r) stacked over b-part rows [r, 2r) -- the part ts::zquatev reads and writes
+ * (reference zquatev.h:40-46); the in-tree analogue in the reference is the residual check test.cc:104-105.
+ * DEVICE pointers; `stream` is a cudaStream_t (NULL = default).
+ *   qgemm      : C (2m x n, ldc) = beta C + alpha op(A) op(B);  ta / tb = 1: the operand is the conjugate transpose of
+ *                the stored array (stored 2k x m / 2n x k).  alpha, beta real.
+ *   congruence : out (2m x m, ldo) = X^H F X  with F 2n x n (structured Fock-like matrix), X 2n x m; work >= 2n x m.
+ *                The back-multiplication C = X C' after the solve is qgemm(0, 0, n, m, m, 1, X, ldx, C', ldc', 0, C, ldc).
+ *   fill_pairing: columns c..2c-1 of a 2r x 2c array from columns 0..c-1 (exact: copy / conjugate / negate).   */
+int zquatev_b200_qgemm(int ta, int tb, int m, int n, int k, double alpha, const void* A, int lda, const void* B, int ldb,
+                       double beta, void* C, int ldc, void* stream);
+int zquatev_b200_congruence(int n, int m, const void* X, int ldx, const void* F, int ldf, void* out, int ldo, void* work,
+                            void* stream);
+int zquatev_b200_fill_pairing(int r, int c, void* M, int ld, void* stream);
+
 /* `batch` independent problems of the same size (BASELINE config 5): problem b uses
  * D + b*strideD (complex elements) and eig + b*strideEig; info[b] receives its return code.
  * Host pointers.  The reference has no batched entry -- its callers loop over zquatev().

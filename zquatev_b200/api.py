@@ -29,6 +29,9 @@ SYMBOLS = {
     "zquatev_b200_reserve": (_I, [_P, _I, ctypes.POINTER(ZqOptions)]),
     "zquatev_b200_workspace_query": (_I, [_I, ctypes.POINTER(ZqOptions), ctypes.POINTER(ctypes.c_ulonglong)]),
     "zquatev_b200_handle_phases": (_I, [_P, _P]),
+    "zquatev_b200_qgemm": (_I, [_I, _I, _I, _I, _I, _D, _P, _I, _P, _I, _D, _P, _I, _P]),
+    "zquatev_b200_congruence": (_I, [_I, _I, _P, _I, _P, _I, _P, _I, _P, _P]),
+    "zquatev_b200_fill_pairing": (_I, [_I, _I, _P, _I, _P]),
     "zquatev_b200_batched": (_I, [_I, _I, _P, _I, _LL, _P, _LL, _P]),
     "zquatev_b200_batched_stats": (None, [_P, _P]),
     "zquatev_b200_release": (None, []),

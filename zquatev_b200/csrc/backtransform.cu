@@ -180,6 +180,17 @@ __global__ void __launch_bounds__(256) k_theta_inplace(int n, cplx* R, size_t ld
   c[n + r] = cconj(u);
 }
 
+// right half from the left half of a structured 2r x 2c array (caller-side helper of zquatev_b200_fill_pairing)
+__global__ void __launch_bounds__(256) k_fill_pairing(int r_, int c_, cplx* M, size_t ld) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= r_) return;
+  const cplx* L = M + (size_t)blockIdx.y * ld;
+  cplx* R = M + (size_t)(c_ + blockIdx.y) * ld;
+  const cplx u = L[r], v = L[r_ + r];
+  R[r] = cneg(cconj(v));
+  R[r_ + r] = cconj(u);
+}
+
 // deterministic split-K reduction: Y = parts[0] + parts[1] + ... (fixed order)
 __global__ void __launch_bounds__(256) k_sum_parts(size_t count, int nparts, const cplx* __restrict__ parts, size_t stride,
                                                    cplx* __restrict__ Y) {
@@ -252,6 +263,11 @@ void launch_swap_pairing(int n, int ncols, cplx* Out, size_t ld, cudaStream_t st
   if (ncols <= 0) return;
   dim3 g((n + 255) / 256, ncols);
   k_swap_pairing<<<g, 256, 0, st>>>(n, Out, ld);
+}
+
+void launch_fill_pairing(int r, int c, cplx* M, size_t ld, cudaStream_t st) {
+  dim3 g((r + 255) / 256, c);
+  k_fill_pairing<<<g, 256, 0, st>>>(r, c, M, ld);
 }
 
 void launch_theta_inplace(int n, int ncols, cplx* R, size_t ld, cudaStream_t st) {

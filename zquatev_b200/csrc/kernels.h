@@ -185,6 +185,8 @@ void launch_scale_Z(int n, int ncols, const double* Z, size_t ldz, const int* pe
 // K10 pairing, in place: X sits in the RIGHT half (columns n..2n-1); on exit the left
 // half holds (U;V) = X and the right half Theta(X) = (-conj V; conj U)
 void launch_swap_pairing(int n, int ncols, cplx* Out, size_t ld, cudaStream_t st);
+// right half (columns c..2c-1) of a structured 2r x 2c array from its left half
+void launch_fill_pairing(int r, int c, cplx* M, size_t ld, cudaStream_t st);
 // R (2n x ncols block of X) <- Theta(R) in place (host-pointer pipeline: X itself has been downloaded already)
 void launch_theta_inplace(int n, int ncols, cplx* R, size_t ld, cudaStream_t st);
 

@@ -13,8 +13,8 @@
 // planes, plus an O(MN) recombination.  Here the eight real products run on the FP64 tensor path (DMMA m8n8k4) with
 // eight accumulator sets per thread; the component sums are formed in registers from the (a, b) complex-pair
 // fragments, and the recombination is the epilogue.  8 instead of 12 DMMAs per quaternion multiply-add.  Accuracy is
-// that of the 3M scheme (normwise, not componentwise): oracle/quat_kernels.py::qmul8 restates it and
-// tests/test_oracle.py checks the back-transformation built on it.
+// that of the 3M scheme (normwise, not componentwise): the test suite holds a numpy restatement (quat_kernels.qgemm8)
+// and checks the back-transformation built on it against the stacked complex form.
 //
 // Operand layout: a quaternion matrix Q = Qa + j Qb is a pair of complex column-major arrays, the b-part `off`
 // elements behind the a-part (the solver's own layout: D/E, Xa/Xb, stacked panels).  Components: q0 = Re Qa,
@@ -23,14 +23,14 @@
 //   TB = 0: B(k,n) = SB[k + n ldb]          TB = 1: B = SB^H, SB stored N x K:  B(k,n) = conj_q(SB[n + k ldb])
 //   C(m,n) <- beta C + alpha A B   (alpha, beta real);  lower != 0: only entries with m >= n are touched.
 // Tiling: CTA = 4 warps (2 x 2), warp tile 16 x 16 quaternions (2 x 2 DMMA fragments x 8 planes = 64 accumulator
-// doubles), CTA tile 32 x 32, BK = 8, 4-stage cp.async pipeline, two CTAs per SM.
+// doubles), CTA tile 32 x 32, BK = 8, 3-stage cp.async pipeline + the C tile staged by cp.async, two CTAs per SM.
 #include "kernels.h"
 #include "gemm_tiles.cuh"
 
 namespace zq {
 namespace {
 
-constexpr int QBM = 32, QBN = 32, QBK = 8, QST = 4, QNT = 128;
+constexpr int QBM = 32, QBN = 32, QNT = 128;
 
 struct QArgs {
   int M, N, K;
@@ -58,8 +58,13 @@ ZQ_D void combos_b(cplx a, cplx b, double (&be)[8]) {
   be[4] = q2 - q3; be[5] = q1 + q0; be[6] = q2 + q3; be[7] = q0 - q1;
 }
 
-template <int TA, int TB>
-__global__ void __launch_bounds__(QNT, 2) k_qgemm8(QArgs p) {
+constexpr int QCLD = QBM + 1;          // column stride of the staged C tile (odd: the epilogue's quarter-warp reads hit 8 bank groups)
+constexpr int QCEL = 2 * QBN * QCLD;   // complex elements of the staged C tile (a-part, b-part)
+
+// CPRE: the C tile (read-modify-write, beta != 0) is fetched into shared memory by cp.async at kernel start, so the
+// epilogue of a short-K product (K6 update: K = 64) does not wait on global loads.
+template <int TA, int TB, int QBK, int QST, int MINB, bool CPRE>
+__global__ void __launch_bounds__(QNT, MINB) k_qgemm8(QArgs p) {
   using TileA = OpTile<QBM, TA == 1, QBK>;
   using TileB = OpTile<QBN, TB == 0, QBK>;
   constexpr int STAGE = 2 * TileA::ELEMS + 2 * TileB::ELEMS;
@@ -87,7 +92,16 @@ __global__ void __launch_bounds__(QNT, 2) k_qgemm8(QArgs p) {
   const int g = lane >> 2, q = lane & 3;
   const bool bzero = (p.beta == 0.0);
 
-  if (!bzero) {   // warm L2 with the C tile this CTA will read-modify-write in the epilogue
+  cplx* sC = smem + (size_t)QST * STAGE;
+  if (CPRE && !bzero) {
+    for (int e = tid; e < 2 * QBN * QBM; e += QNT) {
+      const int r = e % QBM, c = (e / QBM) % QBN, half = e / (QBM * QBN);
+      const bool ok = (r0 + r < p.M) && (c0 + c < p.N);
+      cp_async16(sC + (half * QBN + c) * QCLD + r, ok ? C + (size_t)half * p.coff + (size_t)(r0 + r) + (size_t)(c0 + c) * p.ldc : C, ok);
+    }
+    cp_async_commit();
+  }
+  if (!CPRE && !bzero) {   // warm L2 with the C tile this CTA will read-modify-write in the epilogue
     for (int e = tid; e < QBN * (QBM / 8) * 2; e += QNT) {
       const int half = e / (QBN * (QBM / 8)), f = e % (QBN * (QBM / 8));
       const int c = c0 + f / (QBM / 8), r = r0 + (f % (QBM / 8)) * 8;
@@ -173,7 +187,8 @@ __global__ void __launch_bounds__(QNT, 2) k_qgemm8(QArgs p) {
         cplx* ca = C + (size_t)r + (size_t)c * p.ldc;
         cplx* cb = ca + p.coff;
         if (!bzero) {
-          const cplx oa = *ca, ob = *cb;
+          const cplx oa = CPRE ? sC[(c - c0) * QCLD + (r - r0)] : *ca;
+          const cplx ob = CPRE ? sC[(QBN + c - c0) * QCLD + (r - r0)] : *cb;
           va.x = fma(p.beta, oa.x, va.x); va.y = fma(p.beta, oa.y, va.y);
           vb.x = fma(p.beta, ob.x, vb.x); vb.y = fma(p.beta, ob.y, vb.y);
         }
@@ -183,17 +198,31 @@ __global__ void __launch_bounds__(QNT, 2) k_qgemm8(QArgs p) {
     }
 }
 
-template <int TA, int TB>
-void launch_q(const QArgs& a, int gz, int ncb, cudaStream_t st) {
+template <int TA, int TB, int QBK, int QST, int MINB, bool CPRE>
+void launch_q_cfg(const QArgs& a, int gz, int ncb, cudaStream_t st) {
   using TileA = OpTile<QBM, TA == 1, QBK>;
   using TileB = OpTile<QBN, TB == 0, QBK>;
-  const size_t smem = (size_t)QST * (2 * TileA::ELEMS + 2 * TileB::ELEMS) * sizeof(cplx);
+  const size_t smem = ((size_t)QST * (2 * TileA::ELEMS + 2 * TileB::ELEMS) + (CPRE ? QCEL : 0)) * sizeof(cplx);
   static std::atomic<unsigned long long> attr_done{0};
   if (first_use_on_this_device(attr_done))
-    cudaFuncSetAttribute(k_qgemm8<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_qgemm8<TA, TB, QBK, QST, MINB, CPRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 g((a.M + QBM - 1) / QBM, ncb >= 0 ? 2 * ncb : 2 * ((a.N + 63) / 64), gz);
   if (g.y == 0) return;
-  k_qgemm8<TA, TB><<<g, QNT, smem, st>>>(a);
+  k_qgemm8<TA, TB, QBK, QST, MINB, CPRE><<<g, QNT, smem, st>>>(a);
+}
+
+// ZQ_Q8_CFG (development knob; measured on the 2n = 32768 shapes, profiles/r02_gemm_probe_q8_cfgs.jsonl): 3 (default) BK 8 x
+// 3 stages + the C tile staged in shared memory, 2 CTAs/SM (back-transformation 3074 ms); 0: BK 8 x 4 stages, C read in the
+// epilogue (3226 ms); 1: BK 8 x 3 stages, 3 CTAs/SM under a 168-register cap (3239 ms: the spills cost what the third CTA
+// buys); 2: BK 16 x 2 stages; 4: as 3 with 2 stages and 3 CTAs/SM
+template <int TA, int TB>
+void launch_q(const QArgs& a, int gz, int ncb, cudaStream_t st) {
+  static const int cfg = [] { const char* e = getenv("ZQ_Q8_CFG"); return e ? atoi(e) : 3; }();
+  if (cfg == 1) launch_q_cfg<TA, TB, 8, 3, 3, false>(a, gz, ncb, st);
+  else if (cfg == 2) launch_q_cfg<TA, TB, 16, 2, 2, false>(a, gz, ncb, st);
+  else if (cfg == 0) launch_q_cfg<TA, TB, 8, 4, 2, false>(a, gz, ncb, st);
+  else if (cfg == 4) launch_q_cfg<TA, TB, 8, 2, 3, true>(a, gz, ncb, st);
+  else launch_q_cfg<TA, TB, 8, 3, 2, true>(a, gz, ncb, st);
 }
 
 }  // namespace

@@ -1094,6 +1094,49 @@ int zquatev_b200_ex(int n2, void* D, int ld2, double* eig, const zq_options* opt
   return solve_any(nullptr, n2, D, ld2, eig, opt);
 }
 
+// ---- the step either side of the solver in the caller's workflow: products of quaternion-structured
+// matrices on the device, on the same eight-product quaternion GEMM as K4 / K6.  A structured matrix
+// Phi(Q) = [[Qa, -conj Qb], [Qb, conj Qa]] is passed as its LEFT half (rows [0, r) = Qa, rows [r, 2r) = Qb), exactly the
+// part ts::zquatev reads and writes (zquatev.h:40-46); the right half never has to exist (fill_pairing creates it).
+int zquatev_b200_qgemm(int ta, int tb, int m, int n, int k, double alpha, const void* A, int lda, const void* B, int ldb, double beta,
+                       void* C, int ldc, void* stream) {
+  if (m < 0 || n < 0 || k < 0) return -3;
+  if (!A || !B || !C) return -7;
+  const int ra = ta ? k : m, rb = tb ? n : k;          // rows of the a-part of the stored operands
+  if (lda < 2 * ra || ldb < 2 * rb || ldc < 2 * m) return -8;
+  if (m == 0 || n == 0) return 0;
+  launch_qgemm(ta, tb, m, n, k, alpha, (const cplx*)A, (size_t)lda, (size_t)ra, (const cplx*)B, (size_t)ldb, (size_t)rb, beta, (cplx*)C,
+               (size_t)ldc, (size_t)m, 0, 1, 0, 0, 0, nullptr, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : zq_cuda_fail(e, __FILE__, __LINE__);
+}
+
+// out = X^H F X for structured F (Fock-like, 2n x 2n) and X (2n x 2m): the orthogonalisation step before the eigensolver,
+// and (with zquatev_b200_qgemm(0, 0, ...)) the back-multiplication C = X C' after it.  work: 2n x m complex (ld 2n).
+int zquatev_b200_congruence(int n, int m, const void* X, int ldx, const void* F, int ldf, void* out, int ldo, void* work, void* stream) {
+  if (n < 0 || m < 0) return -1;
+  if (!X || !F || !out || !work) return -3;
+  if (ldx < 2 * n || ldf < 2 * n || ldo < 2 * m) return -4;
+  if (n == 0 || m == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  // W = F X  (n x m quaternion), out = X^H W
+  launch_qgemm(0, 0, n, m, n, 1.0, (const cplx*)F, (size_t)ldf, (size_t)n, (const cplx*)X, (size_t)ldx, (size_t)n, 0.0, (cplx*)work, 2 * (size_t)n,
+               (size_t)n, 0, 1, 0, 0, 0, nullptr, st);
+  launch_qgemm(1, 0, m, m, n, 1.0, (const cplx*)X, (size_t)ldx, (size_t)n, (const cplx*)work, 2 * (size_t)n, (size_t)n, 0.0, (cplx*)out, (size_t)ldo,
+               (size_t)m, 0, 1, 0, 0, 0, nullptr, st);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : zq_cuda_fail(e, __FILE__, __LINE__);
+}
+
+// right half of a structured 2r x 2c array from its left half: columns c + j = (-conj(Qb_j); conj(Qa_j))   (zquatev.cc:93-98)
+int zquatev_b200_fill_pairing(int r, int c, void* M, int ld, void* stream) {
+  if (r < 0 || c < 0 || !M || ld < 2 * r) return -1;
+  if (r == 0 || c == 0) return 0;
+  launch_fill_pairing(r, c, (cplx*)M, (size_t)ld, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : zq_cuda_fail(e, __FILE__, __LINE__);
+}
+
 // ---- handles: explicit workspace ownership (the reference's per-call allocation is zquatev.cc:63-66) ----
 int zquatev_b200_create(zq_handle_t* out) {
   if (!out) return -1;
