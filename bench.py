@@ -41,7 +41,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "2n=%d eigvals+vecs time-to-solution"
-GEMM_EXEC = 0.75 if os.environ.get("ZQ_GEMM_3M", "1") != "0" else 1.0   # executed / canonical GEMM flops
+# executed / canonical GEMM flops of the n >= 1024 kernels: 0.5 for the quaternion 8-product GEMM (8 real products where the
+# canonical count -- 4 complex products of 4 real products -- has 16), 0.75 for the stacked complex 3M form, 1 for 4 products
+GEMM_EXEC = (0.5 if os.environ.get("ZQ_QGEMM", "1") != "0" else (0.75 if os.environ.get("ZQ_GEMM_3M", "1") != "0" else 1.0))
+GEMM_NAME = ("k_qgemm8 (quaternion GEMM, 8 real DMMA products per quaternion product)" if GEMM_EXEC == 0.5 else
+             "k_zgemm_3m (stacked complex GEMM, 3 real products per complex product)" if GEMM_EXEC == 0.75 else "k_zgemm_mma (4 products)")
 REF_SAMPLE_N = 1024          # 2n = 2048 reference run per step (~5-10 s on 16 cores)
 REF_FIT_ZQ = (500, 1024, 2048)   # sizes at which the reference is timed for the power-law fit
 REF_FIT_ZHEEV = (500, 1024)      # zheev(2n) at 2n = 4096 alone is ~5 min on 8 cores: left out of the bounded sample
@@ -470,15 +474,16 @@ def main():
                 "roofline": roof,
                 # second roofline (FP64 tensor path): executed GEMM flops of the back-transformation (32 n^3 / N per rank)
                 # over its CUDA-event time; peak = DMMA rate measured on this pool with tools/fp64_peak.cu
-                "roofline_fp64": {"kernel": "k_zgemm_3m (K6 back-transformation, DMMA m8n8k4, 3 real products per complex product)",
+                "roofline_fp64": {"kernel": "K6 back-transformation: " + GEMM_NAME + ", DMMA m8n8k4",
                                   "bound": "tensor",
-                                  # EXECUTED flops: the 3M scheme performs 3/4 of the canonical 32 n^3 (ZQ_GEMM_3M=0: all of them)
+                                  # EXECUTED DMMA flops: GEMM_EXEC x the canonical 32 n^3 (see GEMM_EXEC above)
+                                  "executed_over_canonical": GEMM_EXEC,
                                   "achieved": GEMM_EXEC * 32.0 * n ** 3 / world / (phases["backtransform"] * 1e-3) * 1e-12 if phases["backtransform"] else None,
                                   "peak": 37.1, "unit": "TFLOP/s",
                                   "frac": GEMM_EXEC * 32.0 * n ** 3 / world / (phases["backtransform"] * 1e-3) * 1e-12 / 37.1 if phases["backtransform"] else None,
                                   "canonical_tflops": 32.0 * n ** 3 / world / (phases["backtransform"] * 1e-3) * 1e-12 if phases["backtransform"] else None,
                                   "peak_source": "own measurement (profiles/r01_fp64_peak.jsonl: DMMA 37.1, DFMA 36.9 TFLOP/s); MEASURED_PEAKS.json has no FP64 entry",
-                                  "note": "phase time includes operand staging, T factors, pairing and (N > 1) the NCCL gather"},
+                                  "note": "achieved / frac = EXECUTED tensor-pipe flops over the phase time (operand staging, T factors, pairing and, for N > 1, the NCCL gather included); canonical_tflops = useful work rate (32 n^3 / t), which exceeds the machine peak because the 8-product scheme needs half the real multiplications; the in-loop component sums (DADD) run on the same physical pipe and are not counted (ncu: profiles/r02_ncu_qgemm.md)"},
                 "cpu_baseline": cpu, "e2e": e2e}
         if k4_ms > 0:
             # third roofline: the trailing rank-2k update [D;E] -= L R^H (K4), event pair around each of its n/nb launches in
@@ -492,7 +497,8 @@ def main():
                     f4 += 32.0 * m * m * kb
             ex = GEMM_EXEC if n >= 1024 else 1.0
             line["roofline_fp64_trailing"] = {
-                "kernel": "k_zgemm_3m<0,1> lower (K4 trailing rank-2k update, DMMA m8n8k4)", "bound": "tensor",
+                "kernel": "K4 trailing rank-2k update, lower: " + (GEMM_NAME if n >= 1024 else "k_zgemm_mma (4 products)") + ", DMMA m8n8k4", "bound": "tensor",
+                "executed_over_canonical": ex,
                 "achieved": ex * f4 / world / (k4_ms * 1e-3) * 1e-12, "peak": 37.1, "unit": "TFLOP/s",
                 "frac": ex * f4 / world / (k4_ms * 1e-3) * 1e-12 / 37.1, "canonical_tflops": f4 / world / (k4_ms * 1e-3) * 1e-12,
                 "note": "per rank: each rank updates the 64-column blocks it owns (1/N of the flops)",
