@@ -42,6 +42,13 @@ for m in (n, n // 2):
     Y = rnd(2 * kb, n)
     L.zq_test_qgemm(1, 0, kb, n, m, 1.0, P.data_ptr(), 2 * m, m, X.data_ptr(), 2 * n, n, 0.0, Y.data_ptr(), 2 * kb, kb, 0, 5, ctypes.byref(ms))
     out.append({"op": "K6 Y=V^H X q8 (no split-K)", "m": m, "ms": round(ms.value, 3), "canonical_tflops": round(fl / ms.value * 1e-9, 2)})
+    # the same two products with two panels merged (K = 128 quaternions for the update, 128 rows of Y)
+    P2, TY2, Y2 = rnd(2 * m, 2 * kb), rnd(4 * kb, n), rnd(4 * kb, n)
+    L.zq_test_qgemm(0, 0, m, n, 2 * kb, -1.0, P2.data_ptr(), 2 * m, m, TY2.data_ptr(), 4 * kb, 2 * kb, 1.0, X.data_ptr(), 2 * n, n, 0, 5, ctypes.byref(ms))
+    out.append({"op": "K6 update q8, two panels merged (K = 128)", "m": m, "ms": round(ms.value, 3), "canonical_tflops": round(2 * fl / ms.value * 1e-9, 2)})
+    L.zq_test_qgemm(1, 0, 2 * kb, n, m, 1.0, P2.data_ptr(), 2 * m, m, X.data_ptr(), 2 * n, n, 0.0, Y2.data_ptr(), 4 * kb, 2 * kb, 0, 5, ctypes.byref(ms))
+    out.append({"op": "K6 Y=V^H X q8, two panels merged (128 rows, no split-K)", "m": m, "ms": round(ms.value, 3), "canonical_tflops": round(2 * fl / ms.value * 1e-9, 2)})
+    del P2, TY2, Y2
     L.zq_test_set_gemm_3m(1)
     Pc = rnd(2 * m, 2 * kb)
     al = (ctypes.c_double * 2)(-1.0, 0.0)

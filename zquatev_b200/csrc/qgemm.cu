@@ -211,17 +211,206 @@ void launch_q_cfg(const QArgs& a, int gz, int ncb, cudaStream_t st) {
   k_qgemm8<TA, TB, QBK, QST, MINB, CPRE><<<g, QNT, smem, st>>>(a);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent variant for the short-K products (K4: K = 128, K6 update: K = 64; no split-K): 2 CTAs per SM loop over the
+// output tiles (round-robin), and the cp.async operand pipeline keeps running ACROSS tile boundaries -- while a tile's
+// epilogue recombines and stores, the first stages of the next tile are already in flight, and the next C tile is
+// fetched into shared memory as soon as the epilogue has read the current one.  Removes the per-tile prologue / epilogue
+// bubbles that leave the shared FP64 pipe 64-74 % busy in the one-tile-per-CTA kernel (profiles/r02_ncu_qgemm.md).
+// ---------------------------------------------------------------------------------------------
+template <int TA, int TB, int QBK, int QST>
+__global__ void __launch_bounds__(QNT, 2) k_qgemm8p(QArgs p, int tiles_m, int tiles_n) {
+  using TileA = OpTile<QBM, TA == 1, QBK>;
+  using TileB = OpTile<QBN, TB == 0, QBK>;
+  constexpr int STAGE = 2 * TileA::ELEMS + 2 * TileB::ELEMS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* smem = reinterpret_cast<cplx*>(smem_raw);
+  cplx* sC = smem + (size_t)QST * STAGE;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 1) * 16, wn = (warp >> 1) * 16;
+  const int g = lane >> 2, q = lane & 3;
+  const bool bzero = (p.beta == 0.0);
+  const int K = p.K, nk = (K + QBK - 1) / QBK;
+  const int T = tiles_m * tiles_n;
+  // tile t -> (r0, c0); false: nothing to do there (beyond N, or above the diagonal of a `lower` product)
+  auto tile_rc = [&](int t, int& r0, int& c0) -> bool {
+    const int tm = t % tiles_m, tn = t / tiles_m;
+    r0 = tm * QBM;
+    c0 = (p.cb0 + (tn >> 1) * p.cbs) * 64 + (tn & 1) * QBN;
+    return c0 < p.N && !(p.lower && r0 + QBM - 1 < c0);
+  };
+  auto next_valid = [&](int t) -> int {
+    int r0, c0;
+    while (t < T && !tile_rc(t, r0, c0)) t += gridDim.x;
+    return t;
+  };
+  auto fetch_c = [&](int t) {          // cp.async of the C tile of tile t (joins the next committed group)
+    int r0, c0;
+    tile_rc(t, r0, c0);
+    for (int e = tid; e < 2 * QBN * QBM; e += QNT) {
+      const int r = e % QBM, c = (e / QBM) % QBN, half = e / (QBM * QBN);
+      const bool ok = (r0 + r < p.M) && (c0 + c < p.N);
+      cp_async16(sC + (half * QBN + c) * QCLD + r, ok ? p.C + (size_t)half * p.coff + (size_t)(r0 + r) + (size_t)(c0 + c) * p.ldc : p.C, ok);
+    }
+  };
+
+  // loader cursor (runs QST - 1 stages ahead of the consumer, across tile boundaries)
+  TileLoader<QBM, TA == 1, QBK, QNT> ldAa, ldAb;
+  TileLoader<QBN, TB == 0, QBK, QNT> ldBa, ldBb;
+  int lt = next_valid((int)blockIdx.x), lkt = 0;
+  unsigned gl = 0;                     // stages issued so far (slot = gl % QST)
+  auto loader_init = [&]() {
+    int r0, c0;
+    tile_rc(lt, r0, c0);
+    ldAa.init(p.A, p.lda, r0, p.M, tid);
+    ldAb.init(p.A + p.aoff, p.lda, r0, p.M, tid);
+    ldBa.init(p.B, p.ldb, c0, p.N, tid);
+    ldBb.init(p.B + p.boff, p.ldb, c0, p.N, tid);
+  };
+  auto issue_next = [&]() {
+    if (lt < T) {
+      cplx* s = smem + (size_t)(gl % QST) * STAGE;
+      ldAa.issue(s, lkt * QBK, K);
+      ldAb.issue(s + TileA::ELEMS, lkt * QBK, K);
+      ldBa.issue(s + 2 * TileA::ELEMS, lkt * QBK, K);
+      ldBb.issue(s + 2 * TileA::ELEMS + TileB::ELEMS, lkt * QBK, K);
+      if (++lkt == nk) {
+        lkt = 0;
+        lt = next_valid(lt + (int)gridDim.x);
+        if (lt < T) loader_init();
+      }
+    }
+    ++gl;
+    cp_async_commit();
+  };
+
+  int ct = lt;                         // consumer cursor
+  if (ct >= T) return;
+  loader_init();
+  if (!bzero) fetch_c(ct);
+#pragma unroll
+  for (int s = 0; s < QST - 1; ++s) issue_next();
+  unsigned gu = 0;                     // stages consumed so far
+
+  while (ct < T) {
+    int r0, c0;
+    tile_rc(ct, r0, c0);
+    double acc[8][2][2][2];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[e][i][j][0] = acc[e][i][j][1] = 0.0;
+    for (int kt = 0; kt < nk; ++kt, ++gu) {
+      cp_async_wait<QST - 2>();
+      __syncthreads();
+      issue_next();
+      const cplx* sAa = smem + (size_t)(gu % QST) * STAGE;
+      const cplx* sAb = sAa + TileA::ELEMS;
+      const cplx* sBa = sAb + TileA::ELEMS;
+      const cplx* sBb = sBa + TileB::ELEMS;
+#pragma unroll
+      for (int k4 = 0; k4 < QBK; k4 += 4) {
+        double al[2][8], be[2][8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          combos_a<TA == 1>(TileA::frag(sAa, wm + 8 * i + g, k4 + q), TileA::frag(sAb, wm + 8 * i + g, k4 + q), al[i]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          combos_b<TB == 1>(TileB::frag(sBa, wn + 8 * j + g, k4 + q), TileB::frag(sBb, wn + 8 * j + g, k4 + q), be[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma(acc[e][i][j][0], acc[e][i][j][1], al[i][e], be[j][e]);
+      }
+    }
+    if (!bzero && nk < QST) {          // very short K: the C tile's group may still be in flight
+      cp_async_wait<0>();
+      __syncthreads();
+    }
+    // epilogue: recombine the eight products; lane holds rows wm+8i+g, columns wn+8j+2q+{0,1}
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + wn + 8 * j + 2 * q + h;
+        if (c >= p.N) continue;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int r = r0 + wm + 8 * i + g;
+          if (r >= p.M || (p.lower && r < c)) continue;
+          const double p1 = acc[0][i][j][h], p2 = acc[1][i][j][h], p3 = acc[2][i][j][h], p4 = acc[3][i][j][h];
+          const double s123 = (p1 + p2) + p3;
+          const double sh = 0.5 * (s123 + p4);
+          const double q0 = (sh - p1) + acc[4][i][j][h];
+          const double q1 = (sh - s123) + acc[5][i][j][h];
+          const double q2 = (sh - p2) + acc[6][i][j][h];
+          const double q3 = (sh - p3) + acc[7][i][j][h];
+          cplx va = cmake(p.alpha * q0, p.alpha * q1);
+          cplx vb = cmake(p.alpha * q2, -p.alpha * q3);
+          cplx* ca = p.C + (size_t)r + (size_t)c * p.ldc;
+          cplx* cb = ca + p.coff;
+          if (!bzero) {
+            const cplx oa = sC[(c - c0) * QCLD + (r - r0)];
+            const cplx ob = sC[(QBN + c - c0) * QCLD + (r - r0)];
+            va.x = fma(p.beta, oa.x, va.x); va.y = fma(p.beta, oa.y, va.y);
+            vb.x = fma(p.beta, ob.x, vb.x); vb.y = fma(p.beta, ob.y, vb.y);
+          }
+          *ca = va;
+          *cb = vb;
+        }
+      }
+    ct = next_valid(ct + (int)gridDim.x);
+    if (!bzero && ct < T) {
+      __syncthreads();                 // every thread has read the staged C tile
+      fetch_c(ct);                     // joins the group committed by the next issue_next()
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int TA, int TB, int QBK, int QST>
+void launch_q_persistent(const QArgs& a, int ncb, cudaStream_t st) {
+  using TileA = OpTile<QBM, TA == 1, QBK>;
+  using TileB = OpTile<QBN, TB == 0, QBK>;
+  const size_t smem = ((size_t)QST * (2 * TileA::ELEMS + 2 * TileB::ELEMS) + QCEL) * sizeof(cplx);
+  static std::atomic<unsigned long long> attr_done{0};
+  static int sms = 0;
+  if (first_use_on_this_device(attr_done)) {
+    cudaFuncSetAttribute(k_qgemm8p<TA, TB, QBK, QST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int tiles_m = (a.M + QBM - 1) / QBM, tiles_n = ncb >= 0 ? 2 * ncb : 2 * ((a.N + 63) / 64);
+  const long total = (long)tiles_m * tiles_n;
+  if (total <= 0) return;
+  const int nsm = sms > 0 ? sms : 148;
+  const int grid = (int)(total < 2L * nsm ? total : 2L * nsm);
+  k_qgemm8p<TA, TB, QBK, QST><<<grid, QNT, smem, st>>>(a, tiles_m, tiles_n);
+}
+
 // ZQ_Q8_CFG (development knob; measured on the 2n = 32768 shapes, profiles/r02_gemm_probe_q8_cfgs.jsonl): 3 (default) BK 8 x
 // 3 stages + the C tile staged in shared memory, 2 CTAs/SM (back-transformation 3074 ms); 0: BK 8 x 4 stages, C read in the
 // epilogue (3226 ms); 1: BK 8 x 3 stages, 3 CTAs/SM under a 168-register cap (3239 ms: the spills cost what the third CTA
-// buys); 2: BK 16 x 2 stages; 4: as 3 with 2 stages and 3 CTAs/SM
+// buys); 2: BK 16 x 2 stages; 4: as 3 with 2 stages and 3 CTAs/SM; 5: BK 16 x 2 stages + staged C tile
 template <int TA, int TB>
 void launch_q(const QArgs& a, int gz, int ncb, cudaStream_t st) {
   static const int cfg = [] { const char* e = getenv("ZQ_Q8_CFG"); return e ? atoi(e) : 3; }();
+  // ZQ_Q8_PERSIST: 1 = persistent CTAs for the plain (one batch, no split-K) products
+  static const int persist = [] { const char* e = getenv("ZQ_Q8_PERSIST"); return e ? atoi(e) : 0; }();
+  if (persist && gz == 1 && a.sk.chunks == 0) {
+    launch_q_persistent<TA, TB, 8, 3>(a, ncb, st);
+    return;
+  }
   if (cfg == 1) launch_q_cfg<TA, TB, 8, 3, 3, false>(a, gz, ncb, st);
   else if (cfg == 2) launch_q_cfg<TA, TB, 16, 2, 2, false>(a, gz, ncb, st);
   else if (cfg == 0) launch_q_cfg<TA, TB, 8, 4, 2, false>(a, gz, ncb, st);
   else if (cfg == 4) launch_q_cfg<TA, TB, 8, 2, 3, true>(a, gz, ncb, st);
+  else if (cfg == 5) launch_q_cfg<TA, TB, 16, 2, 2, true>(a, gz, ncb, st);
   else launch_q_cfg<TA, TB, 8, 3, 2, true>(a, gz, ncb, st);
 }
 
