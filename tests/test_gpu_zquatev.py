@@ -311,6 +311,29 @@ def test_large_golden_vs_reference(n, seed, path):
     assert q["sumsq_relerr"] < 1e-13 and q["trace_err"] <= 1e-13 * n * meta[5]
 
 
+@pytest.mark.parametrize("n,seed", [(1024, 34), (1100, 7), (2050, 33)])
+def test_paired_backtransform_quaternion_path(n, seed, monkeypatch):
+    """n >= 1024: the back-transformation applies two panels per step on the quaternion GEMM (default).  One panel per step
+    (ZQ_BT_PAIR=0) must give the same eigenvectors to rounding; n = 1100 / 2050 leave a ragged last panel and an odd panel count."""
+    import torch
+    import zquatev_b200 as z
+    from tests import gpu_util as G
+    M = O.gen_sym(n, seed)
+    left = torch.from_numpy(np.ascontiguousarray(M[:, :n].T)).cuda()
+    outs = []
+    for pair in ("1", "0"):
+        monkeypatch.setenv("ZQ_BT_PAIR", pair)
+        buf = torch.full((2 * n, 2 * n), float("nan"), dtype=torch.complex128, device="cuda")
+        buf[:n] = left
+        eig = torch.zeros(n, dtype=torch.float64, device="cuda")
+        assert z.zquatev_device(2 * n, buf.data_ptr(), 2 * n, eig.data_ptr()) == 0
+        q = G.device_quality(left, buf, eig, col_chunk=512)
+        assert q["pairing"] == 0.0 and q["residual"] < 0.05 and q["orthogonality"] < 0.9, q
+        outs.append((eig.clone(), buf))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert (outs[0][1] - outs[1][1]).abs().max().item() <= 1e-12
+
+
 @pytest.mark.skipif(os.environ.get("ZQ_TEST_EXPERIMENTAL", "0") == "0",
                     reason="experimental code path, not validated on a GPU yet (set ZQ_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("n,nb", [(130, 64), (200, 64), (500, 64), (300, 20), (90, 7), (1024, 64)])

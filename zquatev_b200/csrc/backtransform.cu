@@ -54,6 +54,47 @@ __global__ void __launch_bounds__(256) k_build_phi_padded(PanelWs w, int j0, int
   P[m_op + ro + (size_t)(kb + t) * ld] = cconj(va);
 }
 
+// Quaternion columns only (no Theta image): Vq[:, t] = (Va_t; Vb_t) of panel j0, a-part rows [0, m_op), b-part rows
+// [m_op, 2 m_op), this panel starting `row_off` rows down (zeros above).  Two calls into adjacent column ranges build the
+// merged panel [V_ja | V_jb] of the two-panel back-transformation on the quaternion GEMM.
+__global__ void __launch_bounds__(256) k_build_vq(PanelWs w, int j0, cplx* Vq, int m_op, int row_off) {
+  const int n = w.n;
+  const int t = blockIdx.y;
+  const int ro = blockIdx.x * 256 + threadIdx.x;
+  if (ro >= m_op) return;
+  const int rr = ro - row_off;
+  cplx va = cmake(0, 0), vb = cmake(0, 0);
+  if (rr == t) va = cmake(1, 0);
+  else if (rr > t) {
+    const size_t r = (size_t)(j0 + 1 + rr), k = (size_t)(j0 + t);
+    va = w.A[r + k * w.lda];
+    vb = w.A[n + r + k * w.lda];
+  }
+  const size_t ld = 2 * (size_t)m_op;
+  Vq[ro + (size_t)t * ld] = va;
+  Vq[m_op + ro + (size_t)t * ld] = vb;
+}
+
+// Phi form (2 Kq x 2 Kq complex, ld 2 Kq, rows / columns ordered [a-parts (Kq) | b-parts (Kq)]) of the merged quaternion T factor
+//   T12_q = [[Ta_q, C_q], [0, Tb_q]],   Kq = ka + kb,
+// from the per-panel Phi forms Ta (2ka x 2ka), Tb (2kb x 2kb) -- whose first columns hold (T_a; T_b) stacked -- and the cross
+// block C_q = -Ta_q (Va^H Vb) Tb_q given stacked (2ka x kb, ld 2ka).
+__global__ void __launch_bounds__(256) k_assemble_T12q(const cplx* __restrict__ Ta, int ka, const cplx* __restrict__ Tb, int kb,
+                                                       const cplx* __restrict__ Cq, cplx* __restrict__ T12) {
+  const int Kq = ka + kb, ld = 2 * Kq;
+  for (int idx = blockIdx.x * 256 + threadIdx.x; idx < Kq * Kq; idx += gridDim.x * 256) {
+    const int r = idx % Kq, c = idx / Kq;
+    cplx a = cmake(0, 0), b = cmake(0, 0);
+    if (r < ka && c < ka) { a = Ta[r + (size_t)c * 2 * ka]; b = Ta[ka + r + (size_t)c * 2 * ka]; }
+    else if (r >= ka && c >= ka) { a = Tb[(r - ka) + (size_t)(c - ka) * 2 * kb]; b = Tb[kb + (r - ka) + (size_t)(c - ka) * 2 * kb]; }
+    else if (r < ka && c >= ka) { a = Cq[r + (size_t)(c - ka) * 2 * ka]; b = Cq[ka + r + (size_t)(c - ka) * 2 * ka]; }
+    T12[r + (size_t)c * ld] = a;
+    T12[Kq + r + (size_t)c * ld] = b;
+    T12[r + (size_t)(Kq + c) * ld] = cneg(cconj(b));
+    T12[Kq + r + (size_t)(Kq + c) * ld] = cconj(a);
+  }
+}
+
 // T12 (Kc x Kc, Kc = 2ka + 2kb, ld Kc) <- [[Ta, 0], [0, Tb]]; the upper-right block is filled by a GEMM afterwards
 __global__ void __launch_bounds__(256) k_assemble_T12(const cplx* __restrict__ Ta, int ka2, const cplx* __restrict__ Tb, int kb2,
                                                       cplx* __restrict__ T12) {
@@ -229,6 +270,16 @@ void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st
 void launch_build_phi_padded(const PanelWs& w, int j0, int kb, cplx* P, int m_op, int row_off, cudaStream_t st) {
   dim3 g((m_op + 255) / 256, kb);
   k_build_phi_padded<<<g, 256, 0, st>>>(w, j0, kb, P, m_op, row_off);
+}
+
+void launch_build_vq(const PanelWs& w, int j0, int kb, cplx* Vq, int m_op, int row_off, cudaStream_t st) {
+  dim3 g((m_op + 255) / 256, kb);
+  k_build_vq<<<g, 256, 0, st>>>(w, j0, Vq, m_op, row_off);
+}
+
+void launch_assemble_T12q(const cplx* Ta, int ka, const cplx* Tb, int kb, const cplx* Cq, cplx* T12, cudaStream_t st) {
+  const int Kq = ka + kb;
+  k_assemble_T12q<<<(Kq * Kq + 255) / 256, 256, 0, st>>>(Ta, ka, Tb, kb, Cq, T12);
 }
 
 void launch_assemble_T12(const cplx* Ta, int ka2, const cplx* Tb, int kb2, cplx* T12, cudaStream_t st) {

@@ -176,6 +176,10 @@ void launch_build_phi(const PanelWs& w, int j0, int kb, cplx* P, cudaStream_t st
 //   merged with, and T12 = [[Ta, 0], [0, Tb]] (the off-diagonal block -Ta (Pa^H Pb) Tb is added by GEMMs)
 void launch_build_phi_padded(const PanelWs& w, int j0, int kb, cplx* P, int m_op, int row_off, cudaStream_t st);
 void launch_assemble_T12(const cplx* Ta, int ka2, const cplx* Tb, int kb2, cplx* T12, cudaStream_t st);
+//   quaternion form of the two-panel step: quaternion columns (Va; Vb) of a panel (zero-padded to m_op rows per half, starting
+//   row_off rows down), and the Phi form of the merged T factor [[Ta_q, C_q], [0, Tb_q]] with C_q given stacked (2ka x kb)
+void launch_build_vq(const PanelWs& w, int j0, int kb, cplx* Vq, int m_op, int row_off, cudaStream_t st);
+void launch_assemble_T12q(const cplx* Ta, int ka, const cplx* Tb, int kb, const cplx* Cq, cplx* T12, cudaStream_t st);
 //   T of every panel (panel j at Tall + j * 4 nb^2: 2kb x 2kb complex, ld 2kb) from saved Gram columns G and tau
 void launch_build_T_all(const PanelWs& w, cplx* Tall, cudaStream_t st);
 //   phase chain s (n quats) from alpha; X0 = diag(s) Z[:, perm]

@@ -400,8 +400,9 @@ void launch_q_persistent(const QArgs& a, int ncb, cudaStream_t st) {
 template <int TA, int TB>
 void launch_q(const QArgs& a, int gz, int ncb, cudaStream_t st) {
   static const int cfg = [] { const char* e = getenv("ZQ_Q8_CFG"); return e ? atoi(e) : 3; }();
-  // ZQ_Q8_PERSIST: 1 = persistent CTAs for the plain (one batch, no split-K) products
-  static const int persist = [] { const char* e = getenv("ZQ_Q8_PERSIST"); return e ? atoi(e) : 0; }();
+  // ZQ_Q8_PERSIST (default 1): persistent CTAs for the plain (one batch, no split-K) products -- K6 update 44.7 -> 47.5, merged
+  // two-panel update 49.7 -> 51.6 canonical TFLOP/s (profiles/r02_gemm_probe_pairs.jsonl)
+  static const int persist = [] { const char* e = getenv("ZQ_Q8_PERSIST"); return e ? atoi(e) : 1; }();
   if (persist && gz == 1 && a.sk.chunks == 0) {
     launch_q_persistent<TA, TB, 8, 3>(a, ncb, st);
     return;

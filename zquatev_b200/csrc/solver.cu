@@ -608,6 +608,65 @@ static void backtransform_pair(Plan* p, cplx* X, size_t ldx, int ncols, int ja, 
   p->launches += 11;
 }
 
+// split-K geometry of a quaternion product with an M x ncols result and K = m: enough pieces for >= 8 waves of 2 CTAs x 148 SMs
+static SplitK q8_splitk(const Plan* p, int M, int ncols, int m) {
+  const size_t ypart = (size_t)2 * M * ncols;
+  const int ctas1 = ((M + 31) / 32) * ((ncols + 31) / 32);
+  int chunks = (8 * 296 + ctas1 - 1) / ctas1;
+  const int cap_mem = (int)(p->yp_elems / ypart), cap_k = m / 256;
+  if (chunks > cap_mem) chunks = cap_mem;
+  if (chunks > 2 * YP_MAX_CHUNKS) chunks = 2 * YP_MAX_CHUNKS;
+  if (chunks > cap_k) chunks = cap_k;
+  if (chunks < 1) chunks = 1;
+  SplitK sk;
+  sk.kc = (((m + chunks - 1) / chunks) + 7) & ~7;
+  sk.chunks = (m + sk.kc - 1) / sk.kc;
+  return sk;
+}
+
+// K6 on the quaternion GEMM with TWO panels ja < jb per step:
+//   H_ja H_jb = I - [Va Vb] [[Ta, -Ta (Va^H Vb) Tb], [0, Tb]] [Va Vb]^H      (Vb zero-padded to the rows of Va),
+// i.e. one merged quaternion panel of width Kq = ka + kb: Y has 128 rows and the update has K = 128, which the GEMM runs 11-14 %
+// faster per flop than the single-panel shapes (profiles/r02_gemm_probe_pairs.jsonl), and X is read / written half as often.
+static void backtransform_pair_q8(Plan* p, cplx* X, size_t ldx, int ncols, int ja, int jb, cudaStream_t st) {
+  const PanelWs& w = p->pw;
+  const int n = w.n, nb = w.nb;
+  const int ka = (nb < n - 1 - ja) ? nb : n - 1 - ja, kb = (nb < n - 1 - jb) ? nb : n - 1 - jb;
+  const int m = n - 1 - ja, off = jb - ja, Kq = ka + kb;
+  const size_t ldp = 2 * (size_t)m;
+  cplx* Vq = p->P;                                         // 2m x Kq, a-parts over b-parts
+  cplx* Vqb = p->P + (size_t)ka * ldp;
+  const cplx* Ta = p->T + (size_t)(ja / nb) * 4 * nb * nb;   // Phi forms; their first columns are (T_a; T_b) stacked
+  const cplx* Tb = p->T + (size_t)(jb / nb) * 4 * nb * nb;
+  cplx* Xa = X + (size_t)(ja + 1);
+  launch_build_vq(w, ja, ka, Vq, m, 0, st);
+  launch_build_vq(w, jb, kb, Vqb, m, off, st);
+  // S_q = Va^H Vb (ka x kb, K = m), stacked 2ka x kb
+  {
+    const SplitK sk = q8_splitk(p, ka, kb, m);
+    const size_t spart = (size_t)2 * ka * kb;
+    launch_qgemm(1, 0, ka, kb, m, 1.0, Vq, ldp, (size_t)m, Vqb, ldp, (size_t)m, 0.0, p->YP, 2 * (size_t)ka, (size_t)ka, 0, 1, 0, 0, spart, &sk, st);
+    launch_sum_parts(spart, sk.chunks, p->YP, spart, p->S12, st);
+  }
+  // C_q = -Ta_q (S_q Tb_q)
+  launch_qgemm(0, 0, ka, kb, kb, 1.0, p->S12, 2 * (size_t)ka, (size_t)ka, Tb, 2 * (size_t)kb, (size_t)kb, 0.0, p->ST, 2 * (size_t)ka, (size_t)ka, 0, 1,
+               0, 0, 0, nullptr, st);
+  launch_qgemm(0, 0, ka, kb, ka, -1.0, Ta, 2 * (size_t)ka, (size_t)ka, p->ST, 2 * (size_t)ka, (size_t)ka, 0.0, p->S12, 2 * (size_t)ka, (size_t)ka, 0, 1,
+               0, 0, 0, nullptr, st);
+  launch_assemble_T12q(Ta, ka, Tb, kb, p->S12, p->T12, st);
+  // Y = [Va Vb]^H X, TY = T12 Y, X -= [Va Vb] TY
+  {
+    const SplitK sk = q8_splitk(p, Kq, ncols, m);
+    const size_t ypart = (size_t)2 * Kq * ncols;
+    launch_qgemm(1, 0, Kq, ncols, m, 1.0, Vq, ldp, (size_t)m, Xa, ldx, (size_t)n, 0.0, p->YP, 2 * (size_t)Kq, (size_t)Kq, 0, 1, 0, 0, ypart, &sk, st);
+    launch_sum_parts(ypart, sk.chunks, p->YP, ypart, p->Y, st);
+  }
+  launch_zgemm(0, 0, 2 * Kq, ncols, 2 * Kq, cmake(1, 0), p->T12, 2 * (size_t)Kq, p->Y, 2 * (size_t)Kq, cmake(0, 0), p->TY, 2 * (size_t)Kq, 0, 1, 0, 0, 0,
+               st);
+  launch_qgemm(0, 0, m, ncols, Kq, -1.0, Vq, ldp, (size_t)m, p->TY, 2 * (size_t)Kq, (size_t)Kq, 1.0, Xa, ldx, (size_t)n, 0, 1, 0, 0, 0, nullptr, st);
+  p->launches += 12;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K6: X <- H_0 ... H_{n-2} X, X = stacked (Xa; Xb), 2n x n, leading dimension ldx
 // ---------------------------------------------------------------------------------------------
@@ -617,10 +676,13 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
   if (n < 2 || ncols <= 0) return;
   const int last = ((n - 2) / nb) * nb;
   const char* pe = getenv("ZQ_BT_PAIR");                 // read at every solve (tests switch it)
-  const bool pair = pe && atoi(pe) != 0;
+  const bool q8 = use_qgemm(n);
+  // two panels per step: default on the quaternion GEMM (n >= 1024), opt-in on the stacked complex path
+  const bool pair = pe ? atoi(pe) != 0 : q8;
   for (int j0 = last; j0 >= 0; j0 -= nb) {
     if (pair && j0 >= nb) {                              // merge this panel with the one before it
-      backtransform_pair(p, X, ldx, ncols, j0 - nb, j0, st);
+      if (q8) backtransform_pair_q8(p, X, ldx, ncols, j0 - nb, j0, st);
+      else backtransform_pair(p, X, ldx, ncols, j0 - nb, j0, st);
       j0 -= nb;
       continue;
     }
