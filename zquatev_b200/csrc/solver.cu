@@ -757,7 +757,7 @@ struct HostSink { cplx* D; size_t ld2; };
 
 // Eigenvector column blocks of the single-GPU host-pointer solve: a large first block, then blocks small enough that
 // (a) the download of block c hides behind the back-transformation of block c+1 (PCIe moves a column ~10x faster than
-// the GEMMs produce one) and (b) only the last, smallest block's download is exposed.  ZQ_E2E_CHUNKS="a,b,c" (column
+// the GEMMs produce one) and (b) only the last, smaller block's download is exposed.  ZQ_E2E_CHUNKS="a,b,c" (column
 // counts, the first absorbs the remainder) overrides.
 static int sink_chunks(int n, int* nc) {
   int cnt = 1;
@@ -779,11 +779,13 @@ static int sink_chunks(int n, int* nc) {
     return cnt;
   }
   if (n < 2048) return 1;
-  int last = n / 16;
+  // two blocks: the download of the first (7/8 of the columns) hides behind the back-transformation of the second, whose own
+  // download (1/8) is what stays exposed.  (Three blocks 13/16 + 1/8 + 1/16 exposed less but cost more: the two-panel
+  // back-transformation is at its best on wide blocks -- measured 2n = 32768: e2e - device 0.21 s with three blocks.)
+  int last = n / 8;
   if (last < 512) last = 512;
   last = (last + 63) & ~63;
-  if (n >= 8192) { nc[0] = n - 3 * last; nc[1] = 2 * last; nc[2] = last; cnt = 3; }
-  else           { nc[0] = n - last; nc[1] = last; cnt = 2; }
+  nc[0] = n - last; nc[1] = last; cnt = 2;
   return cnt;
 }
 
