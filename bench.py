@@ -433,11 +433,12 @@ def main():
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             # H2D: only the lower triangles of A and B travel, in 256-column blocks (upload_lower, csrc/solver.cu)
+            # (N > 1: the same bytes in total, 1/N of them through each rank's host link)
             h2d = sum(2 * (n - c0) * min(256, n - c0) * 16 for c0 in range(0, n, 256)) if n >= 1024 else 16 * n2 * n
             e2e = {"value": te.item(), "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16 * n2 * n2 + 8 * n,
                    "phases_ms": z.last_phases(), "check": e2e_chk,
                    "note": "host-pointer C ABI call zquatev_b200_ex (== ts::zquatev), pinned host array; H2D = lower triangles of (A; B) only; "
-                           "1 GPU: eigenvector column blocks are downloaded on a copy stream while the next block is back-transformed" + ("; every rank uploads its copy of the input, rank 0 downloads all 2n columns, the others their own column blocks" if world > 1 else "")}
+                           "eigenvector column blocks are downloaded on a copy stream while the next block is back-transformed" + ("; N > 1: every rank uploads 1/N of the lower triangles (equal triangle areas) and NVLink carries the rest; each rank back-transforms its column shard in sub-blocks whose exchange (ncclSend/Recv to rank 0) and download overlap the next sub-block; rank 0 downloads all 2n columns, the others their own column blocks (host_result = 1)" if world > 1 else "")}
         except Exception as ex:   # e.g. not enough pinned host memory on the box
             e2e = {"value": None, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
 

@@ -66,7 +66,10 @@ typedef struct zq_options {
   int host_result;   /* dist with host pointers: 0 = every rank downloads all 2n columns (default),
                         1 = rank 0 downloads everything, rank r > 0 only its own eigenvector columns
                         [r*ceil(n/G), ...) and their Kramers partners (the host links are shared by all
-                        GPUs of a box, so G full downloads cost G times one).                      */
+                        GPUs of a box, so G full downloads cost G times one).  Either way the ranks
+                        share the upload (each moves 1/G of the lower triangles, NVLink carries the
+                        rest) and finished column sub-blocks are exchanged and downloaded while the
+                        next ones are back-transformed (ZQ_DIST_PIPE=0 / ZQ_DIST_UPLOAD=0: off).   */
 } zq_options;
 
 /* Same contract as zquatev_b200 plus options.  With jobz = 0 D is destroyed (holds reflectors). */
@@ -183,6 +186,11 @@ void zq_test_set_gemm_3m(int on);
 int zq_test_stedc(int n, const double* d, const double* e, double* w, double* Z);
 /* K9: eigenvalues only by bisection.                                                             */
 int zq_test_bisect(int n, const double* d, const double* e, double* w);
+/* Host-side planners of the collective host-pointer solve (no device needed): widths of the sub-blocks in which every rank
+ * back-transforms its `per` eigenvector columns (returns their number, <= 4; widths sum to per), and the column ranges
+ * [bounds[g], bounds[g+1]) whose lower triangles rank g uploads (world + 1 entries, equal triangle areas).              */
+int zq_test_dist_chunks(int per, int world, int out[4]);
+int zq_test_upload_bounds(int n, int world, int* bounds);
 /* K1-K4: tridiagonalise A (2n x n, lda) in place; outputs d[n], e[n], tau[n], alpha[4n].          */
 int zq_test_tridiag(int n, int nb, void* A, long long lda, double* d, double* e, double* tau, double* alpha);
 

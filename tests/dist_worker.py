@@ -100,6 +100,71 @@ def main():
         same = all(torch.equal(lst[0], t) for t in lst)
         ok = i0 == 0 and i1 == 0 and dev_rel <= 1e-12 and same and bool(torch.all(e_val[1:] >= e_val[:-1]))
         out.append({"transport": "peer", "mode": "values-only", "n": n, "ok": bool(ok), "eig_dev": dev_rel, "ranks_agree": bool(same)})
+    # collective solve with HOST pointers (the reference-shaped entry): shared upload (every rank moves a share of the lower
+    # triangles, NVLink carries the rest), back-transformation in column sub-blocks whose exchange + download overlap the next
+    # sub-block; host_result 0 (every rank gets all 2n columns) and 1 (rank 0 everything, rank r its own columns); also with
+    # the pipeline switched off (gather, then download).  n = 2049: ragged shards (the last rank owns fewer columns).
+    import ctypes
+    for n, seed in [(700, 6), (2048, 32), (2049, 7)]:
+        M = O.gen_sym(n, seed)
+        left = torch.from_numpy(np.ascontiguousarray(M[:, :n].T))
+        left_dev = left.cuda()
+        buf1 = torch.zeros((2 * n, 2 * n), dtype=torch.complex128, device="cuda")
+        buf1[:n] = left_dev
+        eig1 = torch.zeros(n, dtype=torch.float64, device="cuda")
+        i0 = z.zquatev_device(2 * n, buf1.data_ptr(), 2 * n, eig1.data_ptr(), nb=64)          # single-GPU path, this rank
+        q1 = G.device_quality(left_dev, buf1, eig1, col_chunk=512)
+        nrm = eig1.abs().max().item()
+        per = (n + world - 1) // world
+        c0 = min(rank * per, n)
+        nc = max(0, min(per, n - c0))
+        for host_result, pipe in [(1, "1"), (0, "1"), (1, "0")]:
+            os.environ["ZQ_DIST_PIPE"] = pipe
+            host = torch.full((2 * n, 2 * n), float("nan"), dtype=torch.complex128).pin_memory()
+            host[:n] = left
+            eig_h = np.zeros(n)
+            opt = z.ZqOptions(1, 0, 64, None, 1, 0, 0, 1, host_result)
+            info = z.lib().zquatev_b200_ex(2 * n, ctypes.c_void_p(host.data_ptr()), 2 * n, eig_h.ctypes.data, ctypes.byref(opt))
+            torch.cuda.synchronize()
+            dev_rel = float(np.max(np.abs(eig_h - eig1.cpu().numpy())) / nrm)
+            full = host_result == 0 or rank == 0
+            ok = info == 0 and i0 == 0 and dev_rel <= 1e-12
+            rec = {"transport": "peer", "mode": f"host-pointers host_result={host_result} pipe={pipe}", "n": n, "eig_dev": dev_rel}
+            if full:
+                hb = host.cuda()
+                q = G.device_quality(left_dev, hb, torch.from_numpy(eig_h).cuda(), col_chunk=512)
+                ok = ok and q["pairing"] == 0.0 and q["ascending"] and q["residual"] <= max(1.5 * q1["residual"], 0.05) \
+                    and q["orthogonality"] <= max(1.5 * q1["orthogonality"], 1.0)
+                rec.update({"res": q["residual"], "res_single": q1["residual"], "orth": q["orthogonality"], "orth_single": q1["orthogonality"],
+                            "pair": q["pairing"]})
+                del hb
+            else:
+                # own columns and their Kramers partners must be there (finite) and paired exactly
+                own = host[c0:c0 + nc]
+                part = host[n + c0:n + c0 + nc]
+                fin = bool(torch.isfinite(own.view(torch.float64)).all() and torch.isfinite(part.view(torch.float64)).all())
+                pair_ok = bool(torch.equal(part[:, :n], -own[:, n:].conj()) and torch.equal(part[:, n:], own[:, :n].conj()))
+                ok = ok and fin and pair_ok
+                rec.update({"own_cols": [c0, nc], "finite": fin, "paired": pair_ok})
+            # the columns this rank holds agree bit for bit with rank 0's copy of them (checksums over torch.distributed)
+            cs = torch.tensor([float(host[c].real.sum().item()) + float(host[n + c].imag.sum().item()) for c in (c0, c0 + max(nc - 1, 0))]
+                              if nc > 0 else [0.0, 0.0], dtype=torch.float64, device="cuda")
+            ref_cs = torch.zeros((world, 2), dtype=torch.float64, device="cuda")
+            if rank == 0:
+                for r in range(world):
+                    r0 = min(r * per, n)
+                    rn = max(0, min(per, n - r0))
+                    if rn > 0:
+                        ref_cs[r] = torch.tensor([float(host[c].real.sum().item()) + float(host[n + c].imag.sum().item()) for c in (r0, r0 + rn - 1)],
+                                                 dtype=torch.float64, device="cuda")
+            dist.broadcast(ref_cs, 0)
+            mine = ref_cs[rank]
+            same = bool(torch.equal(mine, cs))
+            ok = ok and same
+            rec.update({"ok": bool(ok), "cols_match_rank0": same})
+            out.append(rec)
+            del host
+        os.environ.pop("ZQ_DIST_PIPE", None)
     zd.finalize()
     if rank == 0:
         print("DIST_RESULT " + json.dumps(out), flush=True)

@@ -84,3 +84,37 @@ def test_batch_shards_partition(batch, world):
         cover += list(range(b0, b0 + nb))
         sizes.append(nb)
     assert cover == list(range(batch)) and max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("per,world", [(2048, 8), (4096, 4), (8192, 2), (1024, 8), (1000, 2), (513, 3), (16384, 1), (2050, 2)])
+def test_host_pipeline_chunks(per, world, monkeypatch):
+    """sub-blocks of the collective host-pointer solve: positive widths that sum to the shard, at most 4, the last one
+    (whose download stays exposed) the smallest; small shards are not cut"""
+    monkeypatch.delenv("ZQ_DIST_PIPE", raising=False)
+    monkeypatch.delenv("ZQ_DIST_CHUNKS", raising=False)
+    ch = zd.host_pipeline_chunks(per, world)
+    assert 1 <= len(ch) <= 4 and all(c > 0 for c in ch) and sum(ch) == per
+    if per < 1024:
+        assert ch == [per]
+    else:
+        assert len(ch) >= 2 and ch[-1] == min(ch) and ch[-1] >= 512
+    monkeypatch.setenv("ZQ_DIST_PIPE", "0")
+    assert zd.host_pipeline_chunks(per, world) == [per]
+    monkeypatch.delenv("ZQ_DIST_PIPE")
+    monkeypatch.setenv("ZQ_DIST_CHUNKS", "0,64,32")
+    if per > 96:
+        assert zd.host_pipeline_chunks(per, world) == [per - 96, 64, 32]
+
+
+@pytest.mark.parametrize("n,world", [(16384, 8), (16384, 2), (1024, 2), (2050, 2), (4096, 4), (5000, 3), (1030, 8)])
+def test_upload_ranges_balanced(n, world):
+    """shared upload: the ranges cover [0, n) in order, start on upload-block boundaries, and their lower-triangle
+    areas are balanced (within the rounding to 256-column blocks)"""
+    b = zd.upload_ranges(n, world)
+    assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(world))
+    assert all(x % 256 == 0 for x in b[:-1])
+    area = [sum(n - c for c in range(b[g], b[g + 1])) for g in range(world)]
+    tot = n * (n + 1) // 2
+    assert sum(area) == tot
+    if n >= 8 * 256 * world:
+        assert max(area) <= 1.35 * tot / world

@@ -51,6 +51,8 @@ SYMBOLS = {
     "zq_test_stedc": (_I, [_I, _P, _P, _P, _P]),
     "zq_test_bisect": (_I, [_I, _P, _P, _P]),
     "zq_test_tridiag": (_I, [_I, _I, _P, _LL, _P, _P, _P, _P]),
+    "zq_test_dist_chunks": (_I, [_I, _I, _P]),
+    "zq_test_upload_bounds": (_I, [_I, _I, _P]),
 }
 
 

@@ -34,9 +34,25 @@ inline int count_tiles(int s, int n) {
   return tot;
 }
 
-template <bool FULL>
+// streaming load with an L2 eviction-priority hint (createpolicy evict_first): the 4.3 GB a large mat-vec streams then leave
+// the L2 before the ~70 MB panel (V, W) that col_update / the dot CTAs / reduce_correct re-read at every column
+// (ZQ_K1_EVICT=1; the plain 16-byte load has no direct .L2::evict_first form -- ptxas accepts that only on 256-bit loads)
+ZQ_D unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+ZQ_D cplx ld_stream_hint(const cplx* p, unsigned long long pol) {
+  cplx v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+template <bool EVF>
+ZQ_D cplx ld_mat(const cplx* p, unsigned long long pol) { return EVF ? ld_stream_hint(p, pol) : ld_stream(p); }
+
+template <bool FULL, bool EVF>
 ZQ_D void tile_body(const cplx* __restrict__ A, size_t lda, int n, int r0, int c0, const quat (&vrow)[RI],
-                    const quat* vcol, quat (&acc)[RI], quat* pt_row, int lane, int warp) {
+                    const quat* vcol, quat (&acc)[RI], quat* pt_row, int lane, int warp, unsigned long long pol) {
   const cplx* Dp = A + (size_t)r0 + lane;
   const cplx* Ep = Dp + n;
 #pragma unroll 2
@@ -46,16 +62,16 @@ ZQ_D void tile_body(const cplx* __restrict__ A, size_t lda, int n, int r0, int c
     if (FULL) {
 #pragma unroll
       for (int i = 0; i < RI; ++i) {
-        dv[i] = ld_stream(Dp + (size_t)c * lda + 32 * i);
-        ev[i] = ld_stream(Ep + (size_t)c * lda + 32 * i);
+        dv[i] = ld_mat<EVF>(Dp + (size_t)c * lda + 32 * i, pol);
+        ev[i] = ld_mat<EVF>(Ep + (size_t)c * lda + 32 * i, pol);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < RI; ++i) {
         const int r = r0 + lane + 32 * i;
         const bool ok = (r < n) && (c < n) && (r >= c);
-        dv[i] = ok ? ld_stream(Dp + (size_t)c * lda + 32 * i) : cmake(0, 0);
-        ev[i] = (ok && r > c) ? ld_stream(Ep + (size_t)c * lda + 32 * i) : cmake(0, 0);
+        dv[i] = ok ? ld_mat<EVF>(Dp + (size_t)c * lda + 32 * i, pol) : cmake(0, 0);
+        ev[i] = (ok && r > c) ? ld_mat<EVF>(Ep + (size_t)c * lda + 32 * i, pol) : cmake(0, 0);
       }
     }
     const quat vc = vcol[warp * CW + jj];
@@ -103,6 +119,7 @@ ZQ_D quat refl_v(const quat* x, quat inv, int r, int s, int head, int n) {
 // back, and 1/tpb of the per-CTA prologue / epilogue); the transposed sums go to pt[I][c] per tile as before.
 constexpr int TPB_MAX = K1_TPB_MAX;
 
+template <bool EVF>
 __global__ void __launch_bounds__(256, 2)
 k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* x, int xrec, int head, quat* __restrict__ pd,
          quat* __restrict__ pt, int nI, int R0, int nR, int G, int rank, int tpb, int rev,
@@ -115,6 +132,7 @@ k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* x, in
   quat* vrow_s = reinterpret_cast<quat*>(k1_smem) + NW * TR;
   quat* vcol = vrow_s + TR;
   pdl_enter();
+  const unsigned long long pol = EVF ? l2_evict_first_policy() : 0ull;
   const quat inv = ld_cg_quat(x + xrec + 2);
   if ((int)blockIdx.x >= nI) {
     // ---- panel inner products: the grid cells right of the tile columns, flattened, one per (row chunk, group of
@@ -185,8 +203,8 @@ k_matvec(const cplx* __restrict__ A, size_t lda, int n, int s, const quat* x, in
     if (J > Jmax) break;
     const int c0 = J * TC;
     const bool full = (c0 + TC - 1 < r0) && (r0 + TR <= n);
-    if (full) tile_body<true>(A, lda, n, r0, c0, vrow, vcol + t * TC, acc, pt_row, lane, warp);
-    else      tile_body<false>(A, lda, n, r0, c0, vrow, vcol + t * TC, acc, pt_row, lane, warp);
+    if (full) tile_body<true, EVF>(A, lda, n, r0, c0, vrow, vcol + t * TC, acc, pt_row, lane, warp, pol);
+    else      tile_body<false, EVF>(A, lda, n, r0, c0, vrow, vcol + t * TC, acc, pt_row, lane, warp, pol);
   }
 #pragma unroll
   for (int i = 0; i < RI; ++i) red[warp][lane + 32 * i] = acc[i];
@@ -232,8 +250,16 @@ int k1_tpb(int m, int world) {
 static size_t k1_smem_bytes(int tpb) { return (size_t)(NW * TR + TR + tpb * TC) * sizeof(quat); }
 static void k1_prepare() {
   static std::atomic<unsigned long long> done{0};
-  if (first_use_on_this_device(done))
-    cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(K1_TPB_MAX));
+  if (first_use_on_this_device(done)) {
+    cudaFuncSetAttribute(k_matvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(K1_TPB_MAX));
+    cudaFuncSetAttribute(k_matvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1_smem_bytes(K1_TPB_MAX));
+  }
+}
+// ZQ_K1_EVICT: trailing size from which the matrix loads carry the L2 evict_first hint (0 = never; read at every solve)
+static bool k1_evict(int m) {
+  const char* e = getenv("ZQ_K1_EVICT");
+  const int from = e ? atoi(e) : 0;
+  return from > 0 && m >= from;
 }
 
 // runs of this rank that hold at least one column block J >= J0: first index R0 and count
@@ -261,8 +287,9 @@ void launch_matvec(const PanelWs& w, int k, int j0, cudaStream_t st) {
   const int rev = (zigzag && nR > 0 && ((k - j0) & 1) == 0) ? 1 : 0;
   const int gy = nR > 0 ? nR : 1;
   k1_prepare();
-  launch_chain_smem(k_matvec, dim3(nI + (ndot + gy - 1) / gy, gy), dim3(256), k1_smem_bytes(tpb), st, w.A, w.lda, n, s, (const quat*)w.x, w.xrec, s, w.pd, w.pt, nI, R0,
-               nR, w.world, w.rank, tpb, rev, w.pan, w.nb, ncols, nch > 0 ? nch : 1, crows, w.dotW, w.dotV);
+  launch_chain_smem(k1_evict(n - s) ? k_matvec<true> : k_matvec<false>, dim3(nI + (ndot + gy - 1) / gy, gy), dim3(256), k1_smem_bytes(tpb), st, w.A, w.lda, n, s,
+                    (const quat*)w.x, w.xrec, s, w.pd, w.pt, nI, R0, nR, w.world, w.rank, tpb, rev, w.pan, w.nb, ncols, nch > 0 ? nch : 1, crows, w.dotW,
+                    w.dotV);
 }
 
 void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st, bool gather) {
@@ -273,7 +300,7 @@ void launch_matvec_only(const PanelWs& w, int s, quat* y, cudaStream_t st, bool 
   owned_runs(w, s, tpb, R0, nR);
   // head = -1: no unit head row, v = x * record[2] for all rows >= s
   k1_prepare();
-  k_matvec<<<dim3(nI, nR), 256, k1_smem_bytes(tpb), st>>>(w.A, w.lda, n, s, (const quat*)w.x, w.xrec, -1, w.pd, w.pt, nI, R0, nR, 1, 0, tpb, 0, w.pan, w.nb, 0, 1,
+  (k1_evict(n - s) ? k_matvec<true> : k_matvec<false>)<<<dim3(nI, nR), 256, k1_smem_bytes(tpb), st>>>(w.A, w.lda, n, s, (const quat*)w.x, w.xrec, -1, w.pd, w.pt, nI, R0, nR, 1, 0, tpb, 0, w.pan, w.nb, 0, 1,
                                          DOT_MIN_ROWS, w.dotW, w.dotV);
   if (gather) k_matvec_gather<<<(n - s + 255) / 256, 256, 0, st>>>(n, s, tpb, w.pd, w.pt, y);
 }

@@ -54,6 +54,8 @@ struct Plan {
   cudaStream_t cs = nullptr;         // host-pointer mode: D2H of finished eigenvector column blocks overlaps the next block
   cudaEvent_t ev_chunk[4] = {};      //   block c back-transformed (recorded on the solver's stream, awaited by cs)
   cudaEvent_t ev_copy = nullptr;     //   all downloads issued on cs are complete
+  cudaStream_t gs = nullptr;         // collective host-pointer mode: NCCL gather of the ranks' finished column sub-blocks (so that a
+  cudaEvent_t ev_gath[4] = {};       //   rank busy downloading never delays the others' sends); sub-block c gathered
   cudaEvent_t done = nullptr;        // recorded at the end of every solve: the next user of this workspace waits on it,
   bool done_valid = false;           // so an asynchronous solve on another stream cannot race with it
   double gather_ms = 0;
@@ -74,6 +76,8 @@ struct NcclApi {
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -96,6 +100,7 @@ static int nccl_load() {
   ZQ_SYM(GetUniqueId, "ncclGetUniqueId") ZQ_SYM(CommInitRank, "ncclCommInitRank") ZQ_SYM(CommDestroy, "ncclCommDestroy")
   ZQ_SYM(Broadcast, "ncclBroadcast") ZQ_SYM(AllReduce, "ncclAllReduce") ZQ_SYM(GroupStart, "ncclGroupStart")
   ZQ_SYM(GroupEnd, "ncclGroupEnd") ZQ_SYM(AllGather, "ncclAllGather") ZQ_SYM(GetErrorString, "ncclGetErrorString")
+  ZQ_SYM(Send, "ncclSend") ZQ_SYM(Recv, "ncclRecv")
 #undef ZQ_SYM
   g_nccl.h = h;
   return 0;
@@ -134,6 +139,8 @@ static void plan_free(Plan* p) {
   for (auto& e : p->ev_chunk) if (e) cudaEventDestroy(e);
   if (p->ev_copy) cudaEventDestroy(p->ev_copy);
   if (p->cs) cudaStreamDestroy(p->cs);
+  for (auto& e : p->ev_gath) if (e) cudaEventDestroy(e);
+  if (p->gs) cudaStreamDestroy(p->gs);
   for (auto& e : p->k1ev) cudaEventDestroy(e);
   for (auto& e : p->k4ev) cudaEventDestroy(e);
   delete p;
@@ -218,6 +225,7 @@ static int plan_create(int n, int nb, Plan** out) {
   cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming);
   for (auto& ev : p->ev_chunk) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&p->ev_copy, cudaEventDisableTiming);
+  for (auto& ev : p->ev_gath) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   *out = p;
   return 0;
 }
@@ -753,7 +761,7 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
 // full solve on device-resident operands.  Dfull: 2n x 2n complex (ld), left half = input.
 // Host-pointer mode: where finished eigenvector column blocks go (downloaded on the plan's copy stream while the next
 // block is back-transformed).
-struct HostSink { cplx* D; size_t ld2; };
+struct HostSink { cplx* D; size_t ld2; int host_result; };
 
 // Eigenvector column blocks of the single-GPU host-pointer solve: a large first block, then blocks small enough that
 // (a) the download of block c hides behind the back-transformation of block c+1 (PCIe moves a column ~10x faster than
@@ -787,6 +795,151 @@ static int sink_chunks(int n, int* nc) {
   last = (last + 63) & ~63;
   nc[0] = n - last; nc[1] = last; cnt = 2;
   return cnt;
+}
+
+// Collective host-pointer solve (dist = 1): every rank back-transforms its shard of `per` eigenvector columns in SUB-BLOCKS; a
+// finished sub-block is gathered over NVLink (stream gs) and downloaded (stream cs) while the next one is computed.  Rank 0 (or
+// every rank, host_result = 0) downloads the sub-blocks of ALL `world` ranks, so a downloaded column costs it
+// rho = world * t_pcie / t_backtransform of the time the GEMMs need to produce one (t_pcie ~ 20 us for the 1 MB of a column
+// pair at 2n = 32768, t_backtransform ~ 190 us: rho ~ 0.1 world).  Going backwards from a small last sub-block (its download is
+// what stays exposed) each earlier one may be 1/rho wider and still hide behind its successor; at most 3 sub-blocks -- every
+// extra pass over the panels costs ~30 ms of per-panel fixed work at n = 16384.  The widths are the same on every rank (they
+// only depend on per and world), so the NCCL calls match.  ZQ_DIST_CHUNKS="a,b,c" overrides (first absorbs the remainder);
+// ZQ_DIST_PIPE=0 disables the pipeline (one block, gather, then download: the round-1 behaviour).
+static int dist_sink_chunks(int per, int world, int* nc) {
+  nc[0] = per; nc[1] = nc[2] = nc[3] = 0;
+  if (const char* e = getenv("ZQ_DIST_PIPE")) if (atoi(e) == 0) return 1;
+  if (const char* e = getenv("ZQ_DIST_CHUNKS")) {
+    int v[4] = {0, 0, 0, 0}, k = 0;
+    for (const char* q = e; *q && k < 4;) {
+      v[k++] = atoi(q);
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    int rest = 0, cnt = 1;
+    for (int i = 1; i < k; ++i) rest += v[i] > 0 ? v[i] : 0;
+    if (k >= 1 && rest < per) {
+      cnt = 0;
+      nc[cnt++] = per - rest;
+      for (int i = 1; i < k; ++i) if (v[i] > 0) nc[cnt++] = v[i];
+    }
+    return cnt;
+  }
+  if (per < 1024) return 1;
+  double rho = 0.105 * (world > 1 ? world : 1);
+  if (rho > 0.9) rho = 0.9;
+  int last = (per / 8 + 63) & ~63;
+  if (last < 512) last = 512;
+  int blk[3], cnt = 0, rem = per;
+  int next = ((int)(last / rho) + 63) & ~63;
+  if (rem - last > next + next / 2) {              // three sub-blocks: a middle one only when a clearly larger first one remains
+    blk[cnt++] = last;
+    blk[cnt++] = next;
+    rem -= last + next;
+  } else {                                          // two: the download of the first just hides behind the second
+    last = ((int)(per * rho / (1.0 + rho)) + 63) & ~63;
+    if (last < 512) last = 512;
+    blk[cnt++] = last;
+    rem -= last;
+  }
+  blk[cnt++] = rem;                                 // the first sub-block absorbs the remainder
+  for (int i = 0; i < cnt; ++i) nc[i] = blk[cnt - 1 - i];
+  return cnt;
+}
+
+// Back-transformation + result delivery of the collective host-pointer solve (dist = 1, host pointers, jobz = 1).
+// Rank g owns eigenvector columns [g per, (g+1) per); it back-transforms them in the sub-blocks of dist_sink_chunks.  When
+// sub-block c is final on the solver's stream:
+//   gs : the sub-blocks c of all ranks are exchanged over NVLink -- host_result = 1: grouped ncclSend to rank 0 / ncclRecv on
+//        rank 0 (only rank 0 needs them); host_result = 0: one grouped ncclBroadcast per rank -- landing at their own columns of
+//        the right half of the receiver's staging array, which is free there;
+//   cs : X = (U; V) of the own sub-block -> the caller's left half, Theta(X) formed in place (K10) -> the caller's right half;
+//        then, once the exchange of this sub-block has arrived, the same for the other ranks' pieces (rank 0, or every rank);
+// while the solver's stream back-transforms sub-block c+1.  Only the last sub-block's exchange + download stay exposed.
+// The device's left half keeps the reflectors until the end, so nothing is swapped on the device (the staging array is internal).
+static int deliver_dist_piped(Plan* p, cplx* Dfull, size_t ld, const double* Z, const int* perm, cudaStream_t st, const HostSink* sink) {
+  const PanelWs& w = p->pw;
+  const int n = w.n, G = g_world, per = (n + G - 1) / G;
+  cplx* X = Dfull + (size_t)n * ld;
+  int cnc[4];
+  const int nchunk = dist_sink_chunks(per, G, cnc);
+  const bool all = sink->host_result != 1;          // every rank wants all columns on its host
+  const size_t w16 = (size_t)2 * n * sizeof(cplx);
+  auto piece = [&](int r, int off, int wb, int& c0, int& nc) {   // columns of rank r's sub-block [off, off + wb) of its shard
+    const int lo = r * per + off, hi = (r + 1) * per < n ? (r + 1) * per : n;
+    c0 = lo < hi ? lo : hi;
+    nc = (lo + wb < hi ? lo + wb : hi) - c0;
+    if (nc < 0) nc = 0;
+  };
+  auto download = [&](int c0, int nc) -> int {       // on cs
+    if (nc <= 0) return 0;
+    cplx* Xc = X + (size_t)c0 * ld;
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)c0 * sink->ld2, sink->ld2 * sizeof(cplx), Xc, ld * sizeof(cplx), w16, (size_t)nc,
+                                    cudaMemcpyDeviceToHost, p->cs));
+    launch_theta_inplace(n, nc, Xc, ld, p->cs);
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)(n + c0) * sink->ld2, sink->ld2 * sizeof(cplx), Xc, ld * sizeof(cplx), w16, (size_t)nc,
+                                    cudaMemcpyDeviceToHost, p->cs));
+    p->launches += 1;
+    return 0;
+  };
+  int off = 0;
+  for (int c = 0; c < nchunk; ++c) {
+    const int wb = cnc[c];
+    int my0, mync;
+    piece(g_rank, off, wb, my0, mync);
+    if (mync > 0) {
+      launch_scale_Z(n, mync, Z, (size_t)n, perm + my0, p->s, X + (size_t)my0 * ld, ld, st);
+      backtransform(p, X + (size_t)my0 * ld, ld, mync, st);
+      p->launches += 1;
+    }
+    if (c == nchunk - 1 && p->timing) cudaEventRecord(p->ev[4], st);
+    ZQ_CUDA_CHECK(cudaEventRecord(p->ev_chunk[c], st));
+    ZQ_CUDA_CHECK(cudaStreamWaitEvent(p->gs, p->ev_chunk[c], 0));
+    ZQ_CUDA_CHECK(cudaStreamWaitEvent(p->cs, p->ev_chunk[c], 0));
+    // exchange of the sub-blocks c (the same call sequence on every rank)
+    {
+      ZQ_NCCL_CHECK(g_nccl.GroupStart());
+      ncclResult_t bad = ncclSuccess;               // an error inside the group must not leave it open
+      for (int r = 0; r < G && bad == ncclSuccess; ++r) {
+        int c0, nc;
+        piece(r, off, wb, c0, nc);
+        if (nc <= 0) continue;
+        cplx* Xr = X + (size_t)c0 * ld;
+        const size_t cnt = (size_t)2 * nc * ld;     // doubles: nc whole columns of the staging array (ld = 2n)
+        if (all) {
+          bad = g_nccl.Broadcast(Xr, Xr, cnt, ncclDouble, r, g_comm, p->gs);
+        } else if (r != 0) {
+          if (g_rank == r) bad = g_nccl.Send(Xr, cnt, ncclDouble, 0, g_comm, p->gs);
+          else if (g_rank == 0) bad = g_nccl.Recv(Xr, cnt, ncclDouble, r, g_comm, p->gs);
+        }
+      }
+      const ncclResult_t endr = g_nccl.GroupEnd();
+      ZQ_NCCL_CHECK(bad);
+      ZQ_NCCL_CHECK(endr);
+      ZQ_CUDA_CHECK(cudaEventRecord(p->ev_gath[c], p->gs));
+    }
+    // downloads: own piece at once, the others' after the exchange
+    int rc = download(my0, mync);
+    if (rc) return rc;
+    if (all || g_rank == 0) {
+      ZQ_CUDA_CHECK(cudaStreamWaitEvent(p->cs, p->ev_gath[c], 0));
+      for (int r = 0; r < G; ++r) {
+        if (r == g_rank) continue;
+        int c0, nc;
+        piece(r, off, wb, c0, nc);
+        rc = download(c0, nc);
+        if (rc) return rc;
+      }
+    }
+    off += wb;
+  }
+  // the solver's stream continues (eigenvalues, status) after the last download and the last exchange
+  ZQ_CUDA_CHECK(cudaEventRecord(p->ev_copy, p->cs));
+  ZQ_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_copy, 0));
+  ZQ_CUDA_CHECK(cudaStreamWaitEvent(st, p->ev_gath[nchunk - 1], 0));
+  cudaError_t e2 = cudaGetLastError();
+  if (e2 != cudaSuccess) return zq_cuda_fail(e2, __FILE__, __LINE__);
+  return 0;
 }
 
 static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jobz, int col0, int ncols, int dist, int gather, cudaStream_t st,
@@ -855,6 +1008,7 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
     } else if (ncols <= 0 || col0 < 0 || col0 + ncols > n) { col0 = 0; ncols = n; }
     launch_build_T_all(w, p->T, st);            // compact-WY T factor of every panel, once
     p->launches += 1;
+    if (sink && dist && p->cs && p->gs) return deliver_dist_piped(p, Dfull, ld, Z, perm, st, sink);
     int cnc[4] = {ncols, 0, 0, 0};
     const int nchunk = (sink && !dist && p->cs) ? sink_chunks(ncols, cnc) : 1;
     const bool piped = sink && !dist && p->cs;
@@ -972,14 +1126,10 @@ static int check_args(int n2, void* D, int ld2, double* eig) {
 // column block -- half the bytes of the left half (the reference needs both triangles; for a valid
 // quaternion-Hermitian input they carry the same information).
 constexpr int UP_BLK = 256;
-static int upload_lower(cplx* Dfull, size_t ld, const cplx* D, size_t ld2, int n, cudaStream_t st) {
-  if (n < 1024) {               // small: one strided copy of the left half
-    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(Dfull, ld * sizeof(cplx), D, ld2 * sizeof(cplx), (size_t)2 * n * sizeof(cplx), (size_t)n,
-                                    cudaMemcpyHostToDevice, st));
-    return 0;
-  }
-  for (int c0 = 0; c0 < n; c0 += UP_BLK) {
-    const int nc = (UP_BLK < n - c0) ? UP_BLK : n - c0;
+// columns [ca, cb) (ca a multiple of UP_BLK)
+static int upload_lower_range(cplx* Dfull, size_t ld, const cplx* D, size_t ld2, int n, int ca, int cb, cudaStream_t st) {
+  for (int c0 = ca; c0 < cb; c0 += UP_BLK) {
+    const int nc = (UP_BLK < cb - c0) ? UP_BLK : cb - c0;
     const size_t rows = (size_t)(n - c0);
     ZQ_CUDA_CHECK(cudaMemcpy2DAsync(Dfull + c0 + (size_t)c0 * ld, ld * sizeof(cplx), D + c0 + (size_t)c0 * ld2, ld2 * sizeof(cplx),
                                     rows * sizeof(cplx), (size_t)nc, cudaMemcpyHostToDevice, st));
@@ -988,11 +1138,56 @@ static int upload_lower(cplx* Dfull, size_t ld, const cplx* D, size_t ld2, int n
   }
   return 0;
 }
+static int upload_lower(cplx* Dfull, size_t ld, const cplx* D, size_t ld2, int n, cudaStream_t st) {
+  if (n < 1024) {               // small: one strided copy of the left half
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(Dfull, ld * sizeof(cplx), D, ld2 * sizeof(cplx), (size_t)2 * n * sizeof(cplx), (size_t)n,
+                                    cudaMemcpyHostToDevice, st));
+    return 0;
+  }
+  return upload_lower_range(Dfull, ld, D, ld2, n, 0, n, st);
+}
+
+// Collective solve with host pointers: every rank passes the same input (its own copy), so the upload is shared -- rank g moves
+// the lower triangles of the column range [b_g, b_g+1) through ITS host link, the ranges cut so that the triangle areas are
+// equal (b_g = n (1 - sqrt(1 - g/G)), rounded to upload blocks), and the ranges are then exchanged over NVLink (one grouped
+// ncclBroadcast per range, whole columns of the staging array).  Round 1 had rank 0 upload everything and broadcast it:
+// 80 ms + 12 ms at 2n = 32768 on 8 GPUs.  ZQ_DIST_UPLOAD=0 restores that.
+static void upload_bounds(int n, int G, int* b) {
+  b[0] = 0;
+  for (int g = 1; g < G; ++g) {
+    int c = (int)((double)n * (1.0 - sqrt(1.0 - (double)g / (double)G)));
+    c = ((c + UP_BLK / 2) / UP_BLK) * UP_BLK;
+    if (c < b[g - 1]) c = b[g - 1];
+    if (c > n) c = n;
+    b[g] = c;
+  }
+  b[G] = n;
+}
+static int upload_shared(cplx* Dfull, size_t ld, const cplx* D, size_t ld2, int n, cudaStream_t st) {
+  int b[PX_MAXW + 65];
+  const int G = g_world;
+  if (G > PX_MAXW + 64) return -5;
+  upload_bounds(n, G, b);
+  int rc = upload_lower_range(Dfull, ld, D, ld2, n, b[g_rank], b[g_rank + 1], st);
+  if (rc) return rc;
+  ZQ_NCCL_CHECK(g_nccl.GroupStart());
+  ncclResult_t bad = ncclSuccess;
+  for (int g = 0; g < G && bad == ncclSuccess; ++g) {
+    if (b[g + 1] <= b[g]) continue;
+    cplx* Cg = Dfull + (size_t)b[g] * ld;
+    bad = g_nccl.Broadcast(Cg, Cg, (size_t)2 * (b[g + 1] - b[g]) * ld, ncclDouble, g, g_comm, st);
+  }
+  const ncclResult_t endr = g_nccl.GroupEnd();
+  ZQ_NCCL_CHECK(bad);
+  ZQ_NCCL_CHECK(endr);
+  return 0;
+}
 
 static int plan_host_staging(Plan* p) {
   const size_t n2 = 2 * (size_t)p->n;
   if (!p->Dfull) ZQ_CUDA_CHECK(cudaMalloc(&p->Dfull, n2 * n2 * sizeof(cplx)));
   if (!p->cs) ZQ_CUDA_CHECK(cudaStreamCreateWithFlags(&p->cs, cudaStreamNonBlocking));
+  if (!p->gs) ZQ_CUDA_CHECK(cudaStreamCreateWithFlags(&p->gs, cudaStreamNonBlocking));
   return 0;
 }
 
@@ -1044,14 +1239,24 @@ static int solve_any(Handle* h, int n2, void* D, int ld2, double* eig, const zq_
   rc = plan_host_staging(p);
   if (rc) return rc;
   cudaEventRecord(p->ev[0], st);
-  if (!dist || g_rank == 0 || !g_comm) {
-    rc = upload_lower(p->Dfull, ld, (const cplx*)D, (size_t)ld2, n, st);
+  static const int shared_up = [] { const char* e = getenv("ZQ_DIST_UPLOAD"); return e ? atoi(e) : 1; }();
+  if (dist && g_comm && g_world > 1 && n >= 1024 && shared_up) {
+    rc = upload_shared(p->Dfull, ld, (const cplx*)D, (size_t)ld2, n, st);   // every rank uploads a share, NVLink carries the rest
     if (rc) return rc;
+  } else {
+    if (!dist || g_rank == 0 || !g_comm) {
+      rc = upload_lower(p->Dfull, ld, (const cplx*)D, (size_t)ld2, n, st);
+      if (rc) return rc;
+    }
+    if (dist && g_comm)        // rank 0 uploads once, NVLink carries the input to the others
+      ZQ_NCCL_CHECK(g_nccl.Broadcast(p->Dfull, p->Dfull, (size_t)2 * n * ld, ncclDouble, 0, g_comm, st));
   }
-  if (dist && g_comm)        // the ranks share the host links: rank 0 uploads once, NVLink carries the input to the others
-    ZQ_NCCL_CHECK(g_nccl.Broadcast(p->Dfull, p->Dfull, (size_t)2 * n * ld, ncclDouble, 0, g_comm, st));
-  const HostSink sink{(cplx*)D, (size_t)ld2};
-  const bool piped = jobz && !dist;                // finished column blocks are downloaded while the next is computed
+  const HostSink sink{(cplx*)D, (size_t)ld2, (opt && dist) ? opt->host_result : 0};
+  // finished eigenvector column blocks are downloaded while the next is computed: one GPU (sink_chunks) and, with
+  // ZQ_DIST_PIPE != 0 (default), the collective solve (deliver_dist_piped)
+  const char* dpe = getenv("ZQ_DIST_PIPE");        // read at every solve (tests switch it)
+  const bool dist_piped = jobz && dist && g_comm && g_world > 1 && !(dpe && atoi(dpe) == 0);
+  const bool piped = jobz && (!dist || dist_piped);
   rc = solve_device(p, p->Dfull, ld, p->eig_dev, jobz, 0, 0, dist, 1, st, piped ? &sink : nullptr);
   if (rc) return rc;
   if (jobz && !piped) {
@@ -1529,6 +1734,14 @@ int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, vo
   cudaEventElapsedTime(&t, a, b);
   if (ms) *ms = reps > 0 ? t / reps : 0.0;
   cudaEventDestroy(a); cudaEventDestroy(b);
+  return 0;
+}
+
+// host-side planners of the collective host-pointer solve (pure integer logic: callable without a GPU)
+int zq_test_dist_chunks(int per, int world, int out[4]) { return dist_sink_chunks(per, world, out); }
+int zq_test_upload_bounds(int n, int world, int* bounds) {
+  if (world < 1 || world > PX_MAXW + 64 || !bounds) return -1;
+  upload_bounds(n, world, bounds);
   return 0;
 }
 

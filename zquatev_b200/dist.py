@@ -24,6 +24,25 @@ def batch_shard(rank: int, world: int, batch: int):
     return b0, base + (1 if rank < extra else 0)
 
 
+def host_pipeline_chunks(per: int, world: int):
+    """Widths of the sub-blocks in which every rank back-transforms its `per` eigenvector columns in the collective
+    host-pointer solve (finished sub-blocks are exchanged and downloaded while the next is computed); the planner lives
+    in csrc/solver.cu (dist_sink_chunks), this is its door."""
+    out = (ctypes.c_int * 4)()
+    cnt = api.lib().zq_test_dist_chunks(per, world, out)
+    return [out[i] for i in range(cnt)]
+
+
+def upload_ranges(n: int, world: int):
+    """Column ranges [b[g], b[g+1]) whose lower triangles rank g uploads in the collective host-pointer solve (equal
+    triangle areas; csrc/solver.cu upload_bounds)."""
+    b = (ctypes.c_int * (world + 1))()
+    rc = api.lib().zq_test_upload_bounds(n, world, b)
+    if rc != 0:
+        raise ValueError("world out of range")
+    return list(b)
+
+
 def owner_of_column(k: int, world: int, nb: int = 64) -> int:
     """Rank that owns column k of (D; E) in the 1-D block-cyclic layout of the reduction."""
     return (k // nb) % world
