@@ -22,7 +22,7 @@ namespace zq {
 
 struct MergeDesc { int off, n1, n2; };
 
-struct DcLevel { int first, count, maxnm; };
+struct DcLevel { int first, count, maxnm; bool uniform; };   // uniform: every merge of the level spans maxnm rows, block m at offset m * maxnm
 
 struct DcWs {
   int n = 0;
@@ -405,6 +405,12 @@ __global__ void __launch_bounds__(256) k_dc_final_sort(int n, const double* __re
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ZQ_DC_SPLIT_LEVELS=0: only the top merge is split across the ranks (the round-1 behaviour); read at every solve
+inline bool dc_split_levels() {
+  const char* e = getenv("ZQ_DC_SPLIT_LEVELS");
+  return !(e && atoi(e) == 0);
+}
+
 }  // namespace
 
 static void build_tree(int n, std::vector<std::vector<MergeDesc>>& lv) {
@@ -461,6 +467,9 @@ DcWs* dc_create(int n) {
       const int nm = m.n1 + m.n2;
       dl.maxnm = nm > dl.maxnm ? nm : dl.maxnm;
     }
+    dl.uniform = true;
+    for (size_t i = 0; i < L.size(); ++i)
+      if (L[i].n1 + L[i].n2 != dl.maxnm || L[i].off != (int)i * dl.maxnm) dl.uniform = false;
     ws->levels.push_back(dl);
   }
   for (auto& m : lv[0]) if (m.off > 0) bounds.push_back(m.off);
@@ -532,20 +541,26 @@ int dc_solve(DcWs* ws, int n, const double* d, const double* e, double* wout, do
     k_dc_zhat<<<dim3(cdiv(L.maxnm, 256), L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dlam, ws->wz, ws->pinv, ws->S, ld, ws->zhat);
     k_dc_vectors<<<dim3(L.maxnm, L.count), 128, 0, st>>>(mg, ws->kcnt, ws->zhat, ws->S, ld);
     {
-      // multi-GPU: the top merge (the block is the whole matrix, columns contiguous) is split by column
-      // blocks of the new eigenvector matrix and all-gathered; lower levels are replicated
-      const bool split = dd && dd->world > 1 && L.count == 1 && L.maxnm == n && n % dd->world == 0 && n >= 2048;
-      const int cbeg = split ? dd->rank * (n / dd->world) : 0;
-      const int cend = split ? cbeg + n / dd->world : 0x7fffffff;
-      const int ncolsg = split ? n / dd->world : L.maxnm;
+      // multi-GPU: the merges of the top levels (the top merge, and below it the levels of 2 and 4 equal blocks while a block
+      // still has >= 1024 columns and every rank >= 128 of them) are split by column blocks of the new eigenvector matrix --
+      // rank g multiplies columns [g nm/G, (g+1) nm/G) of EVERY block of the level -- and all-gathered block by block (whole
+      // columns of Qnew: zeros outside the diagonal block); the levels below are replicated
+      const int nm = L.maxnm;
+      const bool split = dd && dd->world > 1 && L.uniform && L.count <= 4 && (long long)nm * L.count == n && nm % dd->world == 0 &&
+                         ((L.count == 1 && n >= 2048) || (L.count > 1 && nm >= 1024 && nm / dd->world >= 128 && dc_split_levels()));
+      const int cbeg = split ? dd->rank * (nm / dd->world) : 0;
+      const int cend = split ? cbeg + nm / dd->world : 0x7fffffff;
+      const int ncolsg = split ? nm / dd->world : L.maxnm;
       const int n1max = (L.maxnm + 1) / 2;
       k_dc_gemm_mma<<<dim3(cdiv(n1max, DG_BM), cdiv(ncolsg, DG_BN), 2 * L.count), 256, DG_ST * DG_STAGE * sizeof(double), st>>>(
           mg, ws->kcnt, ws->acol, Qold, ws->S, Qnew, ld, cbeg, cend);
       k_dc_finish<<<dim3(cdiv(L.maxnm, 256), L.maxnm, L.count), 256, 0, st>>>(mg, ws->kcnt, ws->dfcol, ws->dfval, ws->lam, Qold, Qnew,
                                                                             ld, ws->d, cbeg, cend);
       if (split) {
-        const int rc = dd->allgather(Qnew, (size_t)(n / dd->world) * n, dd->rank, st);
-        if (rc) return rc;
+        for (int m = 0; m < L.count; ++m) {
+          const int rc = dd->allgather(Qnew + (size_t)m * nm * ld, (size_t)(nm / dd->world) * n, dd->rank, st);
+          if (rc) return rc;
+        }
       }
     }
     cur ^= 1;

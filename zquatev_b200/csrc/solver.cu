@@ -494,20 +494,30 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   cudaMemsetAsync(w.e, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.tau, 0, (size_t)n * 8, st);
   cudaMemsetAsync(w.alpha, 0, (size_t)n * sizeof(quat), st);
+  // Look-ahead of the panel exchange (peer transport; ZQ_DIST_EARLY_PUSH=0: off): the owner of the NEXT panel updates that
+  // panel's 64 columns first, pushes them to every rank, and only then runs the rest of its trailing update -- the push
+  // (33 MB x G over NVLink at m = 16384) leaves the critical path.  Safe without a second landing buffer: every rank has
+  // read the current panel's columns before it pushed its last partial mat-vec, which the owner has already summed.
+  static const int early_on = [] { const char* e = getenv("ZQ_DIST_EARLY_PUSH"); return e ? atoi(e) : 1; }();
+  bool pre = false;                                // this panel's exchange was issued at the end of the previous panel
   for (int j0 = 0; j0 < n - 1; j0 += nb) {
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
     const int owner = (j0 / nb) % G;
     // the panel's columns (current only on their owner) go to every rank once; everything per column that depends on
     // them -- x, the reflector scalars, v -- is then formed by every rank itself
     if (use_px) {
-      const unsigned long long pseq = g_seq_base + (unsigned long long)j0 + 1ull;
-      if (owner == g_rank) launch_push_panel(w, px, j0, kb, pseq, st);
-      else launch_wait_panel(px, pseq, st);
+      if (!pre) {
+        const unsigned long long pseq = g_seq_base + (unsigned long long)j0 + 1ull;
+        if (owner == g_rank) launch_push_panel(w, px, j0, kb, pseq, st);
+        else launch_wait_panel(px, pseq, st);
+        p->launches += 1;
+      }
     } else {
       if (owner == g_rank) launch_pack_panel(w, p->apanel, (size_t)n, j0, kb, st);
       ZQ_NCCL_CHECK(g_nccl.Broadcast(p->apanel, p->apanel, (size_t)2 * (2 * MAX_NB_PANEL) * n, ncclDouble, owner, g_comm, st));
+      p->launches += 1;
     }
-    p->launches += 1;
+    pre = false;
     for (int i = 0; i < kb; ++i) {
       const int k = j0 + i, m = n - k - 1;
       launch_col_update(w, k, j0, st);
@@ -532,16 +542,35 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
       const int b0 = r0 / MV_TC, nblk = (m + MV_TC - 1) / MV_TC;
       const int cb0 = ((g_rank - b0 % G) + G) % G;
       const int ncb = cb0 >= nblk ? 0 : (nblk - 1 - cb0) / G + 1;
-      if (use_qgemm(n)) {
-        launch_build_VW(w, r0, kb, p->L, p->R, st);
-        if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
-        launch_qgemm(0, 1, m, m, 2 * kb, -1.0, p->L, 2 * (size_t)m, (size_t)m, p->R, 2 * (size_t)m, (size_t)m, 1.0,
-                     w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, (size_t)n, 1, 1, 0, 0, 0, nullptr, st, cb0, G, ncb);
+      const bool q8 = use_qgemm(n);
+      if (q8) launch_build_VW(w, r0, kb, p->L, p->R, st);
+      else launch_build_LR(w, r0, kb, p->L, p->R, st);
+      if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
+      auto k4 = [&](int c0, int nc) {              // trailing update of the owned blocks c0, c0 + G, ... (nc of them)
+        if (nc <= 0) return;
+        if (q8)
+          launch_qgemm(0, 1, m, m, 2 * kb, -1.0, p->L, 2 * (size_t)m, (size_t)m, p->R, 2 * (size_t)m, (size_t)m, 1.0,
+                       w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, (size_t)n, 1, 1, 0, 0, 0, nullptr, st, c0, G, nc);
+        else
+          launch_zgemm_cb(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
+                          w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, c0, G, nc, st);
+      };
+      const bool early = use_px && early_on && r0 < n - 1;        // a next panel exists (then kb == nb and r0 is its first column)
+      if (early) {
+        const int kbn = (nb < n - 1 - r0) ? nb : n - 1 - r0;
+        const unsigned long long pseq = g_seq_base + (unsigned long long)r0 + 1ull;
+        if (cb0 == 0) {                            // this rank owns the next panel's columns: update them, push, then the rest
+          k4(0, ncb > 0 ? 1 : 0);
+          launch_push_panel(w, px, r0, kbn, pseq, st);
+          k4(G, ncb - 1);
+        } else {
+          k4(cb0, ncb);
+          launch_wait_panel(px, pseq, st);
+        }
+        p->launches += 1;
+        pre = true;
       } else {
-        launch_build_LR(w, r0, kb, p->L, p->R, st);
-        if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
-        launch_zgemm_cb(0, 1, m, m, 4 * kb, cmake(-1, 0), p->L, 2 * (size_t)m, p->R, (size_t)m, cmake(1, 0),
-                        w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, 1, 2, (size_t)m, 0, (size_t)n, cb0, G, ncb, st);
+        k4(cb0, ncb);
       }
       if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb) + 1], st);
       p->launches += 3;
