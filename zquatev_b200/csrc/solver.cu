@@ -498,7 +498,8 @@ static int tridiagonalise_dist(Plan* p, cudaStream_t st) {
   // panel's 64 columns first, pushes them to every rank, and only then runs the rest of its trailing update -- the push
   // (33 MB x G over NVLink at m = 16384) leaves the critical path.  Safe without a second landing buffer: every rank has
   // read the current panel's columns before it pushed its last partial mat-vec, which the owner has already summed.
-  static const int early_on = [] { const char* e = getenv("ZQ_DIST_EARLY_PUSH"); return e ? atoi(e) : 1; }();
+  const char* epe = getenv("ZQ_DIST_EARLY_PUSH");   // read at every solve (every rank must see the same value)
+  const int early_on = epe ? atoi(epe) : 1;
   bool pre = false;                                // this panel's exchange was issued at the end of the previous panel
   for (int j0 = 0; j0 < n - 1; j0 += nb) {
     const int kb = (nb < n - 1 - j0) ? nb : n - 1 - j0;
@@ -1268,7 +1269,8 @@ static int solve_any(Handle* h, int n2, void* D, int ld2, double* eig, const zq_
   rc = plan_host_staging(p);
   if (rc) return rc;
   cudaEventRecord(p->ev[0], st);
-  static const int shared_up = [] { const char* e = getenv("ZQ_DIST_UPLOAD"); return e ? atoi(e) : 1; }();
+  const char* due = getenv("ZQ_DIST_UPLOAD");      // read at every solve (every rank must see the same value)
+  const int shared_up = due ? atoi(due) : 1;
   if (dist && g_comm && g_world > 1 && n >= 1024 && shared_up) {
     rc = upload_shared(p->Dfull, ld, (const cplx*)D, (size_t)ld2, n, st);   // every rank uploads a share, NVLink carries the rest
     if (rc) return rc;
