@@ -901,11 +901,15 @@ static int deliver_dist_piped(Plan* p, cplx* Dfull, size_t ld, const double* Z, 
     nc = (lo + wb < hi ? lo + wb : hi) - c0;
     if (nc < 0) nc = 0;
   };
-  auto download = [&](int c0, int nc) -> int {       // on cs
+  auto download_left = [&](int c0, int nc) -> int {  // on cs: X = (U; V) -> the caller's left half (reads X only)
+    if (nc <= 0) return 0;
+    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)c0 * sink->ld2, sink->ld2 * sizeof(cplx), X + (size_t)c0 * ld, ld * sizeof(cplx), w16,
+                                    (size_t)nc, cudaMemcpyDeviceToHost, p->cs));
+    return 0;
+  };
+  auto download_right = [&](int c0, int nc) -> int { // on cs: X <- Theta(X) in place, -> the caller's right half
     if (nc <= 0) return 0;
     cplx* Xc = X + (size_t)c0 * ld;
-    ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)c0 * sink->ld2, sink->ld2 * sizeof(cplx), Xc, ld * sizeof(cplx), w16, (size_t)nc,
-                                    cudaMemcpyDeviceToHost, p->cs));
     launch_theta_inplace(n, nc, Xc, ld, p->cs);
     ZQ_CUDA_CHECK(cudaMemcpy2DAsync(sink->D + (size_t)(n + c0) * sink->ld2, sink->ld2 * sizeof(cplx), Xc, ld * sizeof(cplx), w16, (size_t)nc,
                                     cudaMemcpyDeviceToHost, p->cs));
@@ -948,16 +952,20 @@ static int deliver_dist_piped(Plan* p, cplx* Dfull, size_t ld, const double* Z, 
       ZQ_NCCL_CHECK(endr);
       ZQ_CUDA_CHECK(cudaEventRecord(p->ev_gath[c], p->gs));
     }
-    // downloads: own piece at once, the others' after the exchange
-    int rc = download(my0, mync);
+    // downloads: X of the own piece at once; its in-place Theta only after the exchange has read it (this rank may be
+    // sending it); then the other ranks' pieces
+    int rc = download_left(my0, mync);
+    if (rc) return rc;
+    ZQ_CUDA_CHECK(cudaStreamWaitEvent(p->cs, p->ev_gath[c], 0));
+    rc = download_right(my0, mync);
     if (rc) return rc;
     if (all || g_rank == 0) {
-      ZQ_CUDA_CHECK(cudaStreamWaitEvent(p->cs, p->ev_gath[c], 0));
       for (int r = 0; r < G; ++r) {
         if (r == g_rank) continue;
         int c0, nc;
         piece(r, off, wb, c0, nc);
-        rc = download(c0, nc);
+        rc = download_left(c0, nc);
+        if (!rc) rc = download_right(c0, nc);
         if (rc) return rc;
       }
     }
