@@ -20,6 +20,7 @@ from zquatev_b200 import dist as zd  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+    short = len(sys.argv) > 2 and sys.argv[2] == "short"       # fewer A/B legs (large rank counts are charged per GPU)
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     world = int(os.environ["WORLD_SIZE"])
@@ -42,7 +43,8 @@ def main():
         torch.cuda.synchronize()
 
     ref_eig = None
-    for env in [{}, {}, {"ZQ_DIST_EARLY_PUSH": "0"}, {"ZQ_DC_SPLIT_LEVELS": "0"}]:
+    for env in ([{}, {}, {"ZQ_DIST_EARLY_PUSH": "0", "ZQ_DC_SPLIT_LEVELS": "0"}] if short else
+                [{}, {}, {"ZQ_DIST_EARLY_PUSH": "0"}, {"ZQ_DC_SPLIT_LEVELS": "0"}]):
         setenv(env)
         work[:n].copy_(left0)
         sync()
@@ -64,7 +66,8 @@ def main():
     host = torch.empty((n2, n2), dtype=torch.complex128, pin_memory=True)
     host0 = left0.cpu()
     eig_h = np.zeros(n2)
-    for env in [{}, {}, {"ZQ_DIST_PIPE": "0", "ZQ_DIST_UPLOAD": "0"}, {"ZQ_DIST_PIPE": "0"}, {"ZQ_DIST_UPLOAD": "0"}]:
+    for env in ([{}, {}, {"ZQ_DIST_PIPE": "0", "ZQ_DIST_UPLOAD": "0"}] if short else
+                [{}, {}, {"ZQ_DIST_PIPE": "0", "ZQ_DIST_UPLOAD": "0"}, {"ZQ_DIST_PIPE": "0"}, {"ZQ_DIST_UPLOAD": "0"}]):
         setenv(env)
         host[:n].copy_(host0)
         sync()
