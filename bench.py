@@ -10,10 +10,12 @@ value   : device-resident (input already in HBM, result left in HBM), max over r
 e2e     : the same solve through the reference-facing C ABI `zquatev_b200_ex` with HOST (pinned)
           buffers: H2D of the left half and D2H of all 2n columns inside the timed region.
 N > 1   : strong scaling (the problem is fixed).  One collective solve: D and E distributed 1-D
-          block-cyclic by 64-column blocks (per column one NCCL broadcast of the reflector and one
-          all-reduce of the partial mat-vec), trailing update on owned blocks only, back-transformation
-          sharded by eigenvector columns, result gathered on every rank; the tridiagonal D&C is
-          replicated.
+          block-cyclic by 64-column blocks; per panel the owner pushes its 64 columns to every rank and per
+          column the partial mat-vecs are exchanged, both as peer-memory stores fused into the panel kernels
+          (CUDA IPC over NVLink; NCCL collectives as fallback); trailing update on owned blocks only;
+          the top three levels of the tridiagonal D&C and the back-transformation are split by eigenvector
+          columns; result gathered on every rank (device-resident) or, with host pointers, exchanged and
+          downloaded sub-block by sub-block while the next sub-block is back-transformed.
 quality : after the timed loop (outside it) the result of the LAST timed solve is checked on the device at the
           full size, on every N: residual ||MV-VL||_F/(N||M||_F eps), orthogonality ||V^H V-I||_F/(N eps), exact
           quaternion pairing, trace, sum of squares, ascending order (the checks of test.cc:104-112); for N > 1

@@ -18,6 +18,7 @@
 #include <vector>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include "kernels.h"
 #include "../../include/zquatev_b200.h"
 
@@ -154,6 +155,20 @@ static bool use_qgemm(int n) {
   static const int on = [] { const char* e = getenv("ZQ_QGEMM"); return e ? atoi(e) : 1; }();
   return on && n >= 1024;
 }
+
+// NVTX ranges around the phases of a solve as the host ENQUEUES them (ZQ_NVTX=1; header-only NVTX 3: a no-op unless a
+// profiler injects itself).  A timeline tool projects them onto the kernels of the solver's stream.
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) {
+    static const bool enabled = [] { const char* e = getenv("ZQ_NVTX"); return e && atoi(e) != 0; }();
+    on = enabled;
+    if (on) nvtxRangePushA(name);
+  }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("ZQ_PDL"); return e ? atoi(e) != 0 : true; }();
@@ -995,12 +1010,15 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
   if (p->timing) cudaEventRecord(p->ev[1], st);
   launch_scale_input(Dfull, ld, n, p->scl, st);     // zlascl analogue: a no-op pass unless max|a| is outside [1e-146, 1e145]
   p->launches += 3;
-  if (dist) {
-    if (!g_comm) return -6;
-    const int rc = tridiagonalise_dist(p, st);
-    if (rc) return rc;
-  } else {
-    tridiagonalise(p, st);
+  {
+    NvtxRange r_("zquatev_b200: tridiagonalisation (K1-K5)");
+    if (dist) {
+      if (!g_comm) return -6;
+      const int rc = tridiagonalise_dist(p, st);
+      if (rc) return rc;
+    } else {
+      tridiagonalise(p, st);
+    }
   }
   launch_check_finite(n, w.d, w.e, p->info_dev, st);
   if (p->timing) cudaEventRecord(p->ev[2], st);
@@ -1032,12 +1050,17 @@ static int solve_device(Plan* p, cplx* Dfull, size_t ld, double* eig_dev, int jo
                 ncclResult_t r = g_nccl.AllGather(buf + (size_t)rank * count, buf, count, ncclDouble, g_comm, s2);
                 return r == ncclSuccess ? 0 : nccl_fail(r, __LINE__);
               }};
-    int rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st, dist ? &dd : nullptr);
+    int rc;
+    {
+      NvtxRange r_("zquatev_b200: tridiagonal divide & conquer (K8)");
+      rc = dc_solve(p->dc, n, w.d, w.e, eig_dev, &Z, &perm, p->info_dev, st, dist ? &dd : nullptr);
+    }
     if (rc) return rc;
     launch_unscale_eig(n, eig_dev, p->scl, st);
     p->launches += dc_launches(p->dc) + 4;
     if (p->timing) cudaEventRecord(p->ev[3], st);
     cplx* X = Dfull + (size_t)n * ld;          // right half is scratch until the pairing
+    NvtxRange r_bt("zquatev_b200: back-transformation + pairing (K6, K10)");
     launch_phase_chain(n, w.alpha, w.e, p->s, st);
     if (dist) {                                 // eigenvector columns split evenly over the ranks
       const int per = (n + g_world - 1) / g_world;
@@ -1230,6 +1253,7 @@ static int plan_host_staging(Plan* p) {
 }
 
 static int solve_any(Handle* h, int n2, void* D, int ld2, double* eig, const zq_options* opt) {
+  NvtxRange r_("zquatev_b200: solve");
   int rc = check_args(n2, D, ld2, eig);
   if (rc) return rc;
   if (n2 == 0) return 0;
@@ -1741,7 +1765,7 @@ double zquatev_b200_last_trailing_ms(void) {
   return p ? p->k4_ms : 0.0;
 }
 
-const char* zquatev_b200_version(void) { return "zquatev_b200 0.2 sm_100a nb=64"; }
+const char* zquatev_b200_version(void) { return "zquatev_b200 0.3 sm_100a nb=64"; }
 
 // ---- test doors ------------------------------------------------------------------------------
 int zq_test_matvec(int n, int s, const void* A, long long lda, const void* v, void* y, int reps, double* ms) {
