@@ -26,6 +26,21 @@ def test_k1_matvec(n, s):
     assert np.max(np.abs(yb[s:] - rb)) <= 1e-13 * scale
 
 
+@pytest.mark.parametrize("n,s", [(130, 7), (700, 333), (1031, 65)])
+def test_k1_matvec_evict_first_hint_is_bitwise_identical(n, s, monkeypatch):
+    """the K1 instantiation whose matrix loads carry the L2 evict_first cache hint (ZQ_K1_EVICT) computes the same bits"""
+    from tests import gpu_util as G
+    M = O.gen_sym(n, 100 + n)
+    rng = np.random.default_rng(n)
+    va = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    vb = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    monkeypatch.delenv("ZQ_K1_EVICT", raising=False)
+    y0 = G.matvec(M, s, va, vb)
+    monkeypatch.setenv("ZQ_K1_EVICT", "1")
+    y1 = G.matvec(M, s, va, vb)
+    assert np.array_equal(y0[0][s:], y1[0][s:]) and np.array_equal(y0[1][s:], y1[1][s:])
+
+
 def test_k1_ignores_upper_triangles():
     from tests import gpu_util as G
     n = 150

@@ -349,3 +349,25 @@ def test_experimental_paired_backtransform(n, nb, monkeypatch):
     assert i0 == 0 and i1 == 0 and np.array_equal(e0[:n], e1[:n])
     assert np.max(np.abs(o0 - o1)) <= 1e-12
     check_quality(M, o1, e1[:n])
+
+
+def test_nvtx_ranges_and_evict_hint_do_not_change_the_result():
+    """development switches that must be behaviour-neutral: NVTX ranges around the phases (ZQ_NVTX=1, a no-op without a
+    profiler) and the L2 evict_first hint of K1 (ZQ_K1_EVICT): a solve in a fresh process with both on reproduces the
+    eigenvalues of this process bit for bit"""
+    import subprocess
+    import sys
+    from tests import gpu_util as GU
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 300
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import zquatev_b200 as z; from oracle import zquatev_oracle as O; "
+            "M = O.gen_sym(%d, 5); buf = np.asfortranarray(M).copy(order='F'); e = np.zeros(2 * %d); info = z.zquatev(2 * %d, buf, 2 * %d, e); "
+            "print('RES ' + json.dumps({'info': info, 'eig': e[:%d].tolist()}))") % (ROOT, n, n, n, n, n)
+    env = dict(os.environ, ZQ_NVTX="1", ZQ_K1_EVICT="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads(r.stdout[r.stdout.index("RES ") + 4:].splitlines()[0])
+    M = O.gen_sym(n, 5)
+    eig, out, info = GU.solve_host(M)
+    assert res["info"] == 0 and info == 0
+    assert np.array_equal(np.array(res["eig"]), eig[:n])
