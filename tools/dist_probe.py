@@ -20,7 +20,8 @@ from zquatev_b200 import dist as zd  # noqa: E402
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-    short = len(sys.argv) > 2 and sys.argv[2] == "short"       # fewer A/B legs (large rank counts are charged per GPU)
+    short = len(sys.argv) > 2 and sys.argv[2] in ("short", "hostonly")   # fewer A/B legs (large rank counts are charged per GPU)
+    hostonly = len(sys.argv) > 2 and sys.argv[2] == "hostonly"           # one device-resident solve (warm-up + reference eigenvalues)
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     world = int(os.environ["WORLD_SIZE"])
@@ -43,7 +44,7 @@ def main():
         torch.cuda.synchronize()
 
     ref_eig = None
-    for env in ([{}, {}, {"ZQ_DIST_EARLY_PUSH": "0", "ZQ_DC_SPLIT_LEVELS": "0"}] if short else
+    for env in ([{}] if hostonly else [{}, {}, {"ZQ_DIST_EARLY_PUSH": "0", "ZQ_DC_SPLIT_LEVELS": "0"}] if short else
                 [{}, {}, {"ZQ_DIST_EARLY_PUSH": "0"}, {"ZQ_DC_SPLIT_LEVELS": "0"}]):
         setenv(env)
         work[:n].copy_(left0)
