@@ -111,6 +111,32 @@ def test_qgemm8(ta, tb, M, N, Kd, lower):
     assert np.max(np.abs(ga - fa)) <= 2e-12 * Kd and np.max(np.abs(gb - fb)) <= 2e-12 * Kd
 
 
+@pytest.mark.parametrize("tb,M,N,Kd,lower", [(1, 100, 100, 128, 1), (1, 67, 67, 40, 1), (0, 200, 77, 64, 0), (0, 5, 3, 2, 0),
+                                             (0, 129, 129, 7, 0), (1, 33, 65, 17, 0), (0, 300, 260, 128, 0), (1, 257, 257, 100, 1),
+                                             (0, 800, 790, 64, 0), (1, 801, 801, 128, 1)])   # > 444 tiles: several tiles per persistent CTA
+def test_qgemm8_precombined_operands(tb, M, N, Kd, lower, monkeypatch):
+    """the variant of the quaternion GEMM whose eight component sums are formed once per operand panel (qgemm8x.cu, ZQ_Q8X=1):
+    against the 2 x 2 complex block form, and to rounding against the in-loop kernel behind the same door"""
+    from tests import gpu_util as G
+    rng = np.random.default_rng(M * 13 + N + Kd)
+    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    sb = (N, Kd) if tb else (Kd, N)
+    Aa, Ab, Ba, Bb, Ca, Cb = cr(M, Kd), cr(M, Kd), cr(*sb), cr(*sb), cr(M, N), cr(M, N)
+    alpha, beta = -1.0, 1.0
+    monkeypatch.setenv("ZQ_Q8X", "0")
+    ya, yb, _ = G.qgemm(0, tb, alpha, Aa, Ab, Ba, Bb, beta, Ca, Cb, lower)
+    monkeypatch.setenv("ZQ_Q8X", "1")
+    ga, gb, _ = G.qgemm(0, tb, alpha, Aa, Ab, Ba, Bb, beta, Ca, Cb, lower)
+    opB = (Ba.conj().T, -Bb.T) if tb else (Ba, Bb)
+    ra, rb = K.qgemm_ref(Aa, Ab, opB[0], opB[1])
+    ra, rb = alpha * ra + beta * Ca, alpha * rb + beta * Cb
+    if lower:
+        mask = np.tril(np.ones((M, N), dtype=bool))
+        ra, rb = np.where(mask, ra, Ca), np.where(mask, rb, Cb)
+    assert np.max(np.abs(ga - ra)) <= 2e-12 * Kd and np.max(np.abs(gb - rb)) <= 2e-12 * Kd
+    assert np.max(np.abs(ga - ya)) <= 1e-13 * Kd and np.max(np.abs(gb - yb)) <= 1e-13 * Kd
+
+
 @pytest.mark.parametrize("name,d,e", list(_tri_cases()))
 def test_k8_stedc_cases(name, d, e):
     from tests import gpu_util as G

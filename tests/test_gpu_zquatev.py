@@ -311,6 +311,35 @@ def test_large_golden_vs_reference(n, seed, path):
     assert q["sumsq_relerr"] < 1e-13 and q["trace_err"] <= 1e-13 * n * meta[5]
 
 
+@pytest.mark.parametrize("n,seed", [(1024, 34), (2050, 33)])
+def test_solver_on_precombined_operand_gemm(n, seed, monkeypatch):
+    """ZQ_Q8X=1: trailing update and the update half of the back-transformation on the pre-combined-operand GEMM
+    (qgemm8x.cu) -- golden eigenvalues of the reference, quality at or below the reference's, and the same
+    eigenvalues as the default kernels to rounding"""
+    import torch
+    import zquatev_b200 as z
+    from tests import gpu_util as G
+    key = f"{n}_{seed}"
+    if "eig_" + key not in LARGE:
+        pytest.skip("golden file lacks this case")
+    gold, meta = LARGE["eig_" + key], LARGE["meta_" + key]
+    M = O.gen_sym(n, seed)
+    left = torch.from_numpy(np.ascontiguousarray(M[:, :n].T)).cuda()
+    res = {}
+    for on in ("0", "1"):
+        monkeypatch.setenv("ZQ_Q8X", on)
+        buf = torch.full((2 * n, 2 * n), float("nan"), dtype=torch.complex128, device="cuda")
+        buf[:n] = left
+        eig = torch.zeros(n, dtype=torch.float64, device="cuda")
+        assert z.zquatev_device(2 * n, buf.data_ptr(), 2 * n, eig.data_ptr()) == 0
+        q = G.device_quality(left, buf, eig, col_chunk=1024)
+        assert np.max(np.abs(eig.cpu().numpy() - gold)) <= EIG_TOL * meta[5]
+        assert q["pairing"] == 0.0 and q["ascending"]
+        assert q["residual"] <= meta[1] and q["orthogonality"] <= meta[2], (on, q, meta[1], meta[2])
+        res[on] = eig.clone()
+    assert (res["0"] - res["1"]).abs().max().item() <= 1e-13 * meta[5]
+
+
 @pytest.mark.parametrize("n,seed", [(1024, 34), (1100, 7), (2050, 33)])
 def test_paired_backtransform_quaternion_path(n, seed, monkeypatch):
     """n >= 1024: the back-transformation applies two panels per step on the quaternion GEMM (default).  One panel per step

@@ -165,6 +165,13 @@ void launch_zgemm_cb(int ta, int tb, int M, int N, int K, cplx alpha, const cplx
 void launch_qgemm(int ta, int tb, int M, int N, int K, double alpha, const cplx* A, size_t lda, size_t aoff, const cplx* B,
                   size_t ldb, size_t boff, double beta, cplx* C, size_t ldc, size_t coff, int lower, int batch, size_t sA,
                   size_t sB, size_t sC, const SplitK* sk, cudaStream_t st, int cb0 = 0, int cbs = 1, int ncb = -1);
+// Development variant (qgemm8x.cu, ZQ_Q8X=1) for products whose operands are both panels (K4, the update half of K6): the
+// eight component sums of every operand are formed once per panel by an elementwise pass (A8, B8: workspaces of
+// qgemm_x_operand_doubles(rows, K) doubles), the product itself has no DADD in its main loop.  ta = 0 only.
+bool qgemm_x_enabled();
+size_t qgemm_x_operand_doubles(int rows_max, int kmax);
+void launch_qgemm_x(int tb, int M, int N, int K, double alpha, const cplx* A, size_t lda, size_t aoff, const cplx* B, size_t ldb,
+                    size_t boff, double beta, cplx* C, size_t ldc, size_t coff, int lower, double* A8, double* B8, cudaStream_t st);
 // K4 operands of the quaternion form: Aq = [V W], Sq = [W V] (rows r0..n-1; each 2m x 2kb complex with the b-part
 // stacked below the a-part, ld 2m), so that  M[r0:, r0:] -= Aq Sq^H
 void launch_build_VW(const PanelWs& w, int r0, int kb, cplx* Aq, cplx* Sq, cudaStream_t st);

@@ -44,19 +44,7 @@ struct QArgs {
   SplitK sk;              // chunks > 0: split-K, part z writes C + z * sC (alpha = 1, beta = 0 expected)
 };
 
-// the eight left / right combinations of the four components (CONJ: quaternion conjugate of the stored element)
-template <bool CONJ>
-ZQ_D void combos_a(cplx a, cplx b, double (&al)[8]) {
-  const double q0 = a.x, q1 = CONJ ? -a.y : a.y, q2 = CONJ ? -b.x : b.x, q3 = CONJ ? b.y : -b.y;
-  al[0] = q3 + q1; al[1] = q0 - q2; al[2] = q0 + q2; al[3] = q3 - q1;
-  al[4] = q3 - q2; al[5] = q1 + q0; al[6] = q0 - q1; al[7] = q3 + q2;
-}
-template <bool CONJ>
-ZQ_D void combos_b(cplx a, cplx b, double (&be)[8]) {
-  const double q0 = a.x, q1 = CONJ ? -a.y : a.y, q2 = CONJ ? -b.x : b.x, q3 = CONJ ? b.y : -b.y;
-  be[0] = q1 + q2; be[1] = q0 + q3; be[2] = q0 - q3; be[3] = q1 - q2;
-  be[4] = q2 - q3; be[5] = q1 + q0; be[6] = q2 + q3; be[7] = q0 - q1;
-}
+// combos_a / combos_b (the eight left / right combinations of the four components) live in gemm_tiles.cuh
 
 constexpr int QCLD = QBM + 1;          // column stride of the staged C tile (odd: the epilogue's quarter-warp reads hit 8 bank groups)
 constexpr int QCEL = 2 * QBN * QCLD;   // complex elements of the staged C tile (a-part, b-part)

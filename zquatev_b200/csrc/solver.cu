@@ -49,6 +49,7 @@ struct Plan {
   DcWs* dc = nullptr;
   cplx* Dfull = nullptr;     // host-pointer mode staging, 2n x 2n
   cplx* apanel = nullptr;    // multi-GPU over the NCCL transport: the current panel's columns [2][64][n] (allocated on first use)
+  double *X8a = nullptr, *X8b = nullptr;   // pre-combined operands of the ZQ_Q8X GEMM variant (qgemm8x.cu; allocated on first use)
   double* eig_dev = nullptr;
   cudaEvent_t ev[6] = {};
   cudaEvent_t ev_gather = nullptr;   // multi-GPU: recorded before the NCCL gather of the eigenvector shards
@@ -133,6 +134,8 @@ static void plan_free(Plan* p) {
   if (p->slab) cudaFree(p->slab);
   if (p->Dfull) cudaFree(p->Dfull);
   if (p->apanel) cudaFree(p->apanel);
+  if (p->X8a) cudaFree(p->X8a);
+  if (p->X8b) cudaFree(p->X8b);
   if (p->dc) dc_destroy(p->dc);
   for (auto& e : p->ev) if (e) cudaEventDestroy(e);
   if (p->ev_gather) cudaEventDestroy(p->ev_gather);
@@ -169,6 +172,19 @@ struct NvtxRange {
   NvtxRange(const NvtxRange&) = delete;
   NvtxRange& operator=(const NvtxRange&) = delete;
 };
+
+// ZQ_Q8X=1: the trailing update and the update half of the back-transformation on the pre-combined-operand GEMM (qgemm8x.cu).
+// Its two operand workspaces (8 planes x 128 x n doubles each) are allocated on first use; false: use k_qgemm8.
+static bool use_q8x(Plan* p) {
+  if (!qgemm_x_enabled() || !use_qgemm(p->n)) return false;
+  if (!p->X8a || !p->X8b) {
+    if (!p->timing) return false;                   // the solve is being captured into a CUDA graph: no allocation now
+    const size_t bytes = qgemm_x_operand_doubles(p->n, 2 * MAX_NB) * sizeof(double);
+    if (!p->X8a && cudaMalloc(&p->X8a, bytes) != cudaSuccess) { cudaGetLastError(); p->X8a = nullptr; return false; }
+    if (!p->X8b && cudaMalloc(&p->X8b, bytes) != cudaSuccess) { cudaGetLastError(); p->X8b = nullptr; return false; }
+  }
+  return true;
+}
 
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("ZQ_PDL"); return e ? atoi(e) != 0 : true; }();
@@ -350,6 +366,7 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
     return;
   }
   if (n >= 2048) l2_window(st, w.pan, 4 * (size_t)nb * n * sizeof(cplx));
+  const bool q8x = use_q8x(p);
   const bool prof = g_profile && p->timing;
   if (prof && p->k1ev.size() < 2 * (size_t)n) {
     const size_t old = p->k1ev.size();
@@ -379,8 +396,12 @@ static void tridiagonalise(Plan* p, cudaStream_t st) {
         // (D + jE)[r0:, r0:] -= [V W] [W V]^H as ONE quaternion product, lower triangles
         launch_build_VW(w, r0, kb, p->L, p->R, st);
         if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
-        launch_qgemm(0, 1, m, m, 2 * kb, -1.0, p->L, 2 * (size_t)m, (size_t)m, p->R, 2 * (size_t)m, (size_t)m, 1.0,
-                     w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, (size_t)n, 1, 1, 0, 0, 0, nullptr, st);
+        if (q8x)
+          launch_qgemm_x(1, m, m, 2 * kb, -1.0, p->L, 2 * (size_t)m, (size_t)m, p->R, 2 * (size_t)m, (size_t)m, 1.0,
+                         w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, (size_t)n, 1, p->X8a, p->X8b, st);
+        else
+          launch_qgemm(0, 1, m, m, 2 * kb, -1.0, p->L, 2 * (size_t)m, (size_t)m, p->R, 2 * (size_t)m, (size_t)m, 1.0,
+                       w.A + (size_t)r0 + (size_t)r0 * w.lda, w.lda, (size_t)n, 1, 1, 0, 0, 0, nullptr, st);
       } else {
         launch_build_LR(w, r0, kb, p->L, p->R, st);
         if (prof) cudaEventRecord(p->k4ev[2 * (j0 / nb)], st);
@@ -716,7 +737,10 @@ static void backtransform_pair_q8(Plan* p, cplx* X, size_t ldx, int ncols, int j
   }
   launch_zgemm(0, 0, 2 * Kq, ncols, 2 * Kq, cmake(1, 0), p->T12, 2 * (size_t)Kq, p->Y, 2 * (size_t)Kq, cmake(0, 0), p->TY, 2 * (size_t)Kq, 0, 1, 0, 0, 0,
                st);
-  launch_qgemm(0, 0, m, ncols, Kq, -1.0, Vq, ldp, (size_t)m, p->TY, 2 * (size_t)Kq, (size_t)Kq, 1.0, Xa, ldx, (size_t)n, 0, 1, 0, 0, 0, nullptr, st);
+  if (use_q8x(p))
+    launch_qgemm_x(0, m, ncols, Kq, -1.0, Vq, ldp, (size_t)m, p->TY, 2 * (size_t)Kq, (size_t)Kq, 1.0, Xa, ldx, (size_t)n, 0, p->X8a, p->X8b, st);
+  else
+    launch_qgemm(0, 0, m, ncols, Kq, -1.0, Vq, ldp, (size_t)m, p->TY, 2 * (size_t)Kq, (size_t)Kq, 1.0, Xa, ldx, (size_t)n, 0, 1, 0, 0, 0, nullptr, st);
   p->launches += 12;
 }
 
@@ -764,8 +788,11 @@ static void backtransform(Plan* p, cplx* X, size_t ldx, int ncols, cudaStream_t 
       launch_sum_parts(ypart, sk.chunks, p->YP, ypart, p->Y, st);
       launch_zgemm(0, 0, 2 * kb, ncols, 2 * kb, cmake(1, 0), p->T + (size_t)(j0 / nb) * 4 * nb * nb, 2 * (size_t)kb, p->Y, 2 * (size_t)kb, cmake(0, 0),
                    p->TY, 2 * (size_t)kb, 0, 1, 0, 0, 0, st);
-      launch_qgemm(0, 0, m, ncols, kb, -1.0, p->P, ldp, (size_t)m, p->TY, 2 * (size_t)kb, (size_t)kb, 1.0, Xa, ldx, (size_t)n, 0, 1, 0, 0, 0,
-                   nullptr, st);
+      if (use_q8x(p))
+        launch_qgemm_x(0, m, ncols, kb, -1.0, p->P, ldp, (size_t)m, p->TY, 2 * (size_t)kb, (size_t)kb, 1.0, Xa, ldx, (size_t)n, 0, p->X8a, p->X8b, st);
+      else
+        launch_qgemm(0, 0, m, ncols, kb, -1.0, p->P, ldp, (size_t)m, p->TY, 2 * (size_t)kb, (size_t)kb, 1.0, Xa, ldx, (size_t)n, 0, 1, 0, 0, 0,
+                     nullptr, st);
       p->launches += 5;
       continue;
     }
@@ -1531,6 +1558,8 @@ int zquatev_b200_workspace_query(int n2, const zq_options* opt, unsigned long lo
   unsigned long long b = plan_slab_bytes(n, nb);
   if (!opt || opt->jobz) b += dc_bytes(n);
   if (!opt || !opt->device_ptrs) b += 16ull * (unsigned long long)n2 * (unsigned long long)n2;
+  if (qgemm_x_enabled() && use_qgemm(n))                                     // operand workspaces of the ZQ_Q8X variant
+    b += 2ull * qgemm_x_operand_doubles(n, 2 * MAX_NB) * sizeof(double);
   *device_bytes = b;
   return 0;
 }
@@ -1838,6 +1867,26 @@ void zq_test_set_gemm_3m(int on) { zgemm_allow_3m(on); }
 int zq_test_qgemm(int ta, int tb, int M, int N, int K, double alpha, const void* A, long long lda, long long aoff, const void* B,
                   long long ldb, long long boff, double beta, void* C, long long ldc, long long coff, int lower, int reps, double* ms) {
   cudaStream_t st = 0;
+  if (qgemm_x_enabled() && ta == 0 && K > 0) {       // ZQ_Q8X=1: the pre-combined-operand variant (qgemm8x.cu) behind the same door
+    double *A8 = nullptr, *B8 = nullptr;
+    ZQ_CUDA_CHECK(cudaMalloc(&A8, qgemm_x_operand_doubles(M, K) * sizeof(double)));
+    ZQ_CUDA_CHECK(cudaMalloc(&B8, qgemm_x_operand_doubles(N, K) * sizeof(double)));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 1 + (reps > 0 ? reps : 0); ++i) {
+      if (i == 1) cudaEventRecord(a, st);
+      launch_qgemm_x(tb, M, N, K, alpha, (const cplx*)A, (size_t)lda, (size_t)aoff, (const cplx*)B, (size_t)ldb, (size_t)boff, beta, (cplx*)C,
+                     (size_t)ldc, (size_t)coff, lower, A8, B8, st);
+    }
+    cudaEventRecord(b, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && reps > 0 && ms) { float t = 0; cudaEventElapsedTime(&t, a, b); *ms = t / reps; }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(A8); cudaFree(B8);
+    ZQ_CUDA_CHECK(e);
+    ZQ_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   launch_qgemm(ta, tb, M, N, K, alpha, (const cplx*)A, (size_t)lda, (size_t)aoff, (const cplx*)B, (size_t)ldb, (size_t)boff, beta, (cplx*)C,
                (size_t)ldc, (size_t)coff, lower, 1, 0, 0, 0, nullptr, st);
   if (reps > 0) {
