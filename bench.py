@@ -79,9 +79,8 @@ def cpu_reference_points(ref, O, n_target, known=None):
     the BASELINE.md 3 sizes, fits a*n^p to each, extrapolates to n_target.  `known`: {n: seconds} already measured."""
     known = dict(known or {})
     pts = []
-    for nn in REF_FIT_ZQ:
-        if nn > n_target:
-            continue
+    sizes = [nn for nn in REF_FIT_ZQ if nn <= n_target] or [n_target]   # a workload below the smallest fit size is its own sample
+    for nn in sizes:
         M = O.gen_testcc(nn)[2] if nn == 500 else O.gen_sym(nn, 32)      # n = 500: the test.cc matrix itself (config 1)
         if nn in known:
             tz = known[nn]
