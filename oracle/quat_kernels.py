@@ -396,6 +396,41 @@ def qgemm8(Aa, Ab, Ba, Bb):
     return q_from_components([(s - p1) + p5, (s - s123) + p6, (s - p2) + p7, (s - p3) + p8])
 
 
+def q8_planes_a(Aa, Ab, row_pad=32, k_pad=8):
+    """csrc/qgemm8x.cu k_combine_a: the eight LEFT component sums of A (M x K quaternions) as real planes
+    A8[e][k][m], rows zero-padded to a multiple of 32 and k to a multiple of 8 (combos_a of gemm_tiles.cuh)."""
+    a1, a2, a3, a4 = q_components(Aa, Ab)
+    sums = [a4 + a2, a1 - a3, a1 + a3, a4 - a2, a4 - a3, a2 + a1, a1 - a2, a4 + a3]
+    M, Kd = Aa.shape
+    ld, k8 = -(-M // row_pad) * row_pad, -(-Kd // k_pad) * k_pad
+    A8 = np.zeros((8, k8, ld))
+    for e, pl in enumerate(sums):
+        A8[e, :Kd, :M] = pl.T
+    return A8
+
+
+def q8_planes_b(Ba, Bb, col_pad=32, k_pad=8):
+    """csrc/qgemm8x.cu k_combine_b: the eight RIGHT component sums of B (K x N quaternions) as real planes B8[e][k][n]."""
+    b1, b2, b3, b4 = q_components(Ba, Bb)
+    sums = [b2 + b3, b1 + b4, b1 - b4, b2 - b3, b3 - b4, b2 + b1, b3 + b4, b1 - b2]
+    Kd, N = Ba.shape
+    ld, k8 = -(-N // col_pad) * col_pad, -(-Kd // k_pad) * k_pad
+    B8 = np.zeros((8, k8, ld))
+    for e, pl in enumerate(sums):
+        B8[e, :Kd, :N] = pl
+    return B8
+
+
+def qgemm8_planes(A8, B8, M, N):
+    """csrc/qgemm8x.cu k_qgemm8x: eight plain real products of the pre-combined planes (the zero padding contributes
+    nothing) and the recombination of qgemm.cu's epilogue.  Returns (Ca, Cb) of the M x N quaternion product."""
+    p = [A8[e].T @ B8[e] for e in range(8)]
+    s123 = (p[0] + p[1]) + p[2]
+    s = 0.5 * (s123 + p[3])
+    Ca, Cb = q_from_components([(s - p[0]) + p[4], (s - s123) + p[5], (s - p[1]) + p[6], (s - p[2]) + p[7]])
+    return Ca[:M, :N], Cb[:M, :N]
+
+
 def qgemm_ref(Aa, Ab, Ba, Bb):
     """the same product through the complex 2 x 2 block form Phi(A) (Ba; Bb) (what zgemm.cu's stacked GEMMs compute)"""
     return Aa @ Ba - c(Ab) @ Bb, Ab @ Ba + c(Aa) @ Bb

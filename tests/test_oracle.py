@@ -206,3 +206,26 @@ def test_qgemm8_restatement_and_backtransform():
         res[name] = O.quality(M, out, w)
     assert res["q8"][2] == 0.0
     assert res["q8"][0] <= 1.5 * res["stacked"][0] + 0.01 and res["q8"][1] <= 1.5 * res["stacked"][1] + 0.05, res
+
+
+def test_qgemm8_precombined_planes_restatement():
+    """the pre-combined-operand form of the eight-product GEMM (csrc/qgemm8x.cu: component sums once per operand into zero-padded
+    real planes, eight plain real products, recombination) equals the in-loop form and the 2 x 2 complex block product --
+    also for the conjugate-transposed right operand of the trailing update and for ragged sizes (padding)"""
+    rng = np.random.default_rng(8)
+    cr = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    for (M, N, Kd) in [(13, 11, 9), (32, 64, 8), (67, 67, 40), (5, 3, 2)]:
+        Aa, Ab, Ba, Bb = cr(M, Kd), cr(M, Kd), cr(Kd, N), cr(Kd, N)
+        A8, B8 = K.q8_planes_a(Aa, Ab), K.q8_planes_b(Ba, Bb)
+        assert A8.shape[1] % 8 == 0 and A8.shape[2] % 32 == 0 and B8.shape[2] % 32 == 0
+        ga, gb = K.qgemm8_planes(A8, B8, M, N)
+        ra, rb = K.qgemm_ref(Aa, Ab, Ba, Bb)
+        fa, fb = K.qgemm8(Aa, Ab, Ba, Bb)
+        assert np.max(np.abs(ga - ra)) < 1e-12 and np.max(np.abs(gb - rb)) < 1e-12
+        assert np.max(np.abs(ga - fa)) < 1e-13 and np.max(np.abs(gb - fb)) < 1e-13
+        # trailing update: right operand = quaternion conjugate transpose of a stored N x K array S
+        Sa, Sb = cr(N, Kd), cr(N, Kd)
+        opa, opb = np.conj(Sa).T, -Sb.T
+        ga, gb = K.qgemm8_planes(A8, K.q8_planes_b(opa, opb), M, N)
+        ra, rb = K.qgemm_ref(Aa, Ab, opa, opb)
+        assert np.max(np.abs(ga - ra)) < 1e-12 and np.max(np.abs(gb - rb)) < 1e-12
