@@ -28,6 +28,15 @@ def _worker(rank, world, port, q):
         # the ranks also agree on who owns what
         n = 1000
         blocks = [zd.column_block(r, world, n) for r in range(world)]
+        # ... and on the plans of the collective host-pointer solve (every rank must issue the same NCCL call sequence):
+        # sub-block widths of a shard and the upload ranges, computed by each rank's own library call
+        chunks = zd.host_pipeline_chunks(8192, world)
+        ranges = zd.upload_ranges(16384, world)
+        plan = torch.tensor(chunks + [0] * (4 - len(chunks)) + ranges, dtype=torch.int64)
+        plans = [torch.zeros_like(plan) for _ in range(world)]
+        dist.all_gather(plans, plan)
+        assert all(torch.equal(plans[0], p) for p in plans), plans
+        assert sum(chunks) == 8192 and ranges[0] == 0 and ranges[-1] == 16384
         t = torch.tensor([sum(raw) % 65521, blocks[rank][0], blocks[rank][1]], dtype=torch.int64)
         gathered = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
