@@ -161,7 +161,7 @@ double zquatev_b200_last_trailing_ms(void);
  * (dist = 1) solve -- part of phase [3]; 0 for single-GPU solves.                                       */
 double zquatev_b200_last_gather_ms(void);
 
-/* Library build info, e.g. "zquatev_b200 0.2 sm_100a nb=64".                                   */
+/* Library build info, e.g. "zquatev_b200 0.3 sm_100a nb=64".                                   */
 const char* zquatev_b200_version(void);
 
 /* ---- kernel-level test doors (device pointers; used only by tests/ and bench.py) ------------ */
